@@ -1,0 +1,187 @@
+/*
+ * lfm_cuda.h -- C ABI of libfm_cuda.so, the B200 (sm_100a) replacement for the
+ * native half of LightFM's fit_partial / predict hot path.
+ *
+ * Every entry point below replaces one Python-visible function of the
+ * reference's Cython extension (lightfm/_lightfm_fast.pyx.template, "T:").
+ * A maintainer binds them with ctypes from lightfm/_lightfm_fast.py
+ * (see INTEGRATION.md); signatures use plain pointers and sizes only.
+ *
+ *   T:145-182   cdef class CSRMatrix         -> lfm_csr   (borrowed view)
+ *   T:185-259   cdef class FastLightFM       -> lfm_model (borrowed view of the 12 arrays)
+ *   T:694-781   fit_logistic                 -> lfm_fit_logistic
+ *   T:784-912   fit_warp                     -> lfm_fit_warp
+ *   T:915-1071  fit_warp_kos                 -> lfm_fit_warp_kos
+ *   T:1074-1182 fit_bpr                      -> lfm_fit_bpr
+ *   T:1185-1229 predict_lightfm              -> lfm_predict_lightfm
+ *   T:1232-1323 predict_ranks                -> lfm_predict_ranks
+ *   T:1326-1376 calculate_auc_from_rank      -> lfm_calculate_auc_from_rank
+ *   T:1380-1385 __test_in_positives          -> lfm_test_in_positives
+ *
+ * Conventions
+ *   - All "host" entry points take HOST pointers owned by the caller (numpy /
+ *     scipy buffers).  They copy inputs to the GPU, launch the kernels, copy
+ *     the mutated arrays back and return when the host buffers are up to date
+ *     -- exactly the in-place contract of the Cython functions.
+ *   - Return value: LFM_OK (0) or a negative lfm_status; lfm_last_error() gives
+ *     the message of the last failure on the calling thread.  There is NO CPU
+ *     fallback: without a usable CUDA device every compute entry point returns
+ *     LFM_ERR_CUDA.
+ *   - num_threads keeps its slot from the reference signature.  On the GPU it
+ *     selects the execution mode (overridable with lfm_set_mode):
+ *        num_threads == 1  -> LFM_MODE_REPLAY : one sequential stream, the
+ *                             reference's exact order, rand_r stream and
+ *                             per-element arithmetic (bit-reproducible);
+ *        num_threads  > 1  -> LFM_MODE_HOGWILD: one warp per interaction,
+ *                             lock-free concurrent updates (the reference's
+ *                             OpenMP semantics, scaled to the whole GPU).
+ */
+#ifndef LFM_CUDA_H
+#define LFM_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    LFM_OK = 0,
+    LFM_ERR_ARG = -1,   /* bad argument (null pointer, negative size, shape mismatch) */
+    LFM_ERR_CUDA = -2,  /* CUDA runtime / driver failure, or no device */
+    LFM_ERR_OOM = -3,   /* device allocation failed */
+    LFM_ERR_STATE = -4  /* call order / handle misuse */
+} lfm_status;
+
+typedef enum {
+    LFM_MODE_AUTO = 0,    /* decide from num_threads (1 -> replay, >1 -> hogwild) */
+    LFM_MODE_REPLAY = 1,
+    LFM_MODE_HOGWILD = 2
+} lfm_mode;
+
+/* Borrowed view of a scipy CSR matrix (T:145-166). `data` may be NULL where the
+ * callee only needs the structure (positives lookup, rank structure). */
+typedef struct {
+    const int32_t *indptr;  /* [rows + 1] */
+    const int32_t *indices; /* [nnz]      */
+    const float *data;      /* [nnz]      */
+    int32_t rows;
+    int32_t cols;
+    int64_t nnz;
+} lfm_csr;
+
+/* Borrowed view of the model state, the "FitModel layout" (T:185-259, built at
+ * lightfm.py:422-445).  All arrays are C-contiguous float32. */
+typedef struct {
+    float *item_features;          /* [n_item_features, no_components] */
+    float *item_feature_gradients; /* Adagrad / Adadelta accumulator   */
+    float *item_feature_momentum;  /* Adadelta only                    */
+    float *item_biases;            /* [n_item_features]                */
+    float *item_bias_gradients;
+    float *item_bias_momentum;
+    float *user_features;          /* [n_user_features, no_components] */
+    float *user_feature_gradients;
+    float *user_feature_momentum;
+    float *user_biases;            /* [n_user_features]                */
+    float *user_bias_gradients;
+    float *user_bias_momentum;
+    int32_t n_item_features;
+    int32_t n_user_features;
+    int32_t no_components;
+    int32_t adadelta;              /* 0 = adagrad, 1 = adadelta        */
+    float learning_rate;
+    float rho;
+    float eps;
+    int32_t max_sampled;
+} lfm_model;
+
+/* Per-call work counters (algorithmic bytes are computed from them). */
+typedef struct {
+    int64_t positives;        /* rows actually trained on (Y > 0 for warp/bpr)        */
+    int64_t negatives_drawn;  /* S_total: negative items scored                       */
+    int64_t updates;          /* U_total: gradient steps applied                      */
+    int64_t rejected;         /* violating draws discarded because in_positives       */
+    double kernel_ms;         /* device time of the training kernel(s), CUDA events   */
+    double h2d_ms, d2h_ms;    /* copy time inside the call                            */
+    int64_t h2d_bytes, d2h_bytes;
+    int32_t kernel_launches;  /* kernels of this library launched by the call         */
+    int32_t mode;             /* lfm_mode actually used                               */
+} lfm_counters;
+
+/* ---- library state ------------------------------------------------------- */
+const char *lfm_last_error(void);
+const char *lfm_version(void);
+/* Number of usable CUDA devices (0 on a CPU-only box; never fails). */
+int lfm_device_count(void);
+/* Select the device used by the host entry points of this thread (default 0). */
+int lfm_set_device(int device);
+/* Override the num_threads -> mode mapping (LFM_MODE_AUTO restores it). */
+int lfm_set_mode(int mode);
+int lfm_get_mode(void);
+/* Free the cached device staging buffers held by the host entry points. */
+int lfm_release_cache(void);
+
+/* ---- host entry points: the drop-in boundary ------------------------------ */
+
+/* T:694-781.  no_examples = len(Y).  `counters` may be NULL. */
+int lfm_fit_logistic(const lfm_csr *item_features, const lfm_csr *user_features,
+                     const int32_t *user_ids, const int32_t *item_ids,
+                     const float *Y, const float *sample_weight,
+                     const int32_t *shuffle_indices, int64_t no_examples,
+                     lfm_model *model, double item_alpha, double user_alpha,
+                     int32_t num_threads, lfm_counters *counters);
+
+/* T:784-912.  `random_states` are the per-thread rand_r seeds the reference
+ * draws with random_state.randint(0, INT32_MAX, size=num_threads) (T:812-814);
+ * replay mode consumes random_states[0] as the rand_r stream, hogwild mode
+ * hashes all of them into its Philox key. */
+int lfm_fit_warp(const lfm_csr *item_features, const lfm_csr *user_features,
+                 const lfm_csr *interactions,
+                 const int32_t *user_ids, const int32_t *item_ids,
+                 const float *Y, const float *sample_weight,
+                 const int32_t *shuffle_indices, int64_t no_examples,
+                 lfm_model *model, double item_alpha, double user_alpha,
+                 int32_t num_threads, const uint32_t *random_states,
+                 int32_t n_random_states, lfm_counters *counters);
+
+/* T:915-1071.  no_examples = len(user_ids). */
+int lfm_fit_warp_kos(const lfm_csr *item_features, const lfm_csr *user_features,
+                     const lfm_csr *data, const int32_t *user_ids,
+                     const int32_t *shuffle_indices, int64_t no_examples,
+                     lfm_model *model, double item_alpha, double user_alpha,
+                     int32_t k, int32_t n, int32_t num_threads,
+                     const uint32_t *random_states, int32_t n_random_states,
+                     lfm_counters *counters);
+
+/* T:1074-1182. */
+int lfm_fit_bpr(const lfm_csr *item_features, const lfm_csr *user_features,
+                const lfm_csr *interactions,
+                const int32_t *user_ids, const int32_t *item_ids,
+                const float *Y, const float *sample_weight,
+                const int32_t *shuffle_indices, int64_t no_examples,
+                lfm_model *model, double item_alpha, double user_alpha,
+                int32_t num_threads, const uint32_t *random_states,
+                int32_t n_random_states, lfm_counters *counters);
+
+/* T:1185-1229.  Fills predictions[0..no_examples). */
+int lfm_predict_lightfm(const lfm_csr *item_features, const lfm_csr *user_features,
+                        const int32_t *user_ids, const int32_t *item_ids,
+                        float *predictions, int64_t no_examples,
+                        const lfm_model *model, int32_t num_threads);
+
+/* T:1232-1323.  Accumulates into ranks[0..test.nnz) (caller pre-zeroes, lightfm.py:968-975). */
+int lfm_predict_ranks(const lfm_csr *item_features, const lfm_csr *user_features,
+                      const lfm_csr *test_interactions, const lfm_csr *train_interactions,
+                      float *ranks, const lfm_model *model, int32_t num_threads);
+
+/* T:1326-1376.  Sorts rank_data in place per row, fills auc[0..ranks.rows). */
+int lfm_calculate_auc_from_rank(const lfm_csr *ranks, const int32_t *num_train_positives,
+                                float *rank_data, float *auc, int32_t num_threads);
+
+/* T:1380-1385 (test hook; runs the device membership search). Returns 0/1, <0 on error. */
+int lfm_test_in_positives(int32_t row, int32_t col, const lfm_csr *mat);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LFM_CUDA_H */

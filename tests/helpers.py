@@ -1,0 +1,162 @@
+"""Shared test helpers: synthetic problems + a uniform driver for any backend
+exposing the reference's native-module surface (CSRMatrix, FastLightFM, fit_*)."""
+import os
+import sys
+import types
+
+import numpy as np
+import scipy.sparse as sp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+MODEL_ARRAYS = ["item_embeddings", "item_embedding_gradients", "item_embedding_momentum",
+                "item_biases", "item_bias_gradients", "item_bias_momentum",
+                "user_embeddings", "user_embedding_gradients", "user_embedding_momentum",
+                "user_biases", "user_bias_gradients", "user_bias_momentum"]
+
+
+def synthetic_interactions(n_users, n_items, nnz, seed, signed=False):
+    """De-duplicated COO with skewed user activity / item popularity."""
+    rng = np.random.default_rng(seed)
+    u = np.floor(n_users * rng.random(int(nnz * 1.3)) ** 1.5).astype(np.int64)
+    i = np.floor(n_items * rng.random(int(nnz * 1.3)) ** 2.0).astype(np.int64)
+    key = np.unique(u * n_items + i)
+    rng.shuffle(key)
+    key = key[:nnz]
+    rows = (key // n_items).astype(np.int32)
+    cols = (key % n_items).astype(np.int32)
+    if signed:
+        data = np.where(rng.random(len(key)) < 0.5, 1.0, -1.0).astype(np.float32)
+    else:
+        data = np.ones(len(key), dtype=np.float32)
+    return sp.coo_matrix((data, (rows, cols)), shape=(n_users, n_items), dtype=np.float32)
+
+
+def tag_features(n_rows, n_tags, per_row, seed, identity=True, normalize=True):
+    """hstack([I, tags]) CSR float32 with Zipf-ish tags, rows L1-normalised."""
+    rng = np.random.default_rng(seed)
+    cols = np.minimum((n_tags * rng.random((n_rows, per_row)) ** 2.5).astype(np.int64), n_tags - 1)
+    r = np.repeat(np.arange(n_rows), per_row)
+    tags = sp.coo_matrix((np.ones(r.size, np.float32), (r, cols.ravel())),
+                         shape=(n_rows, n_tags)).tocsr()
+    tags.sum_duplicates()
+    tags.data[:] = 1.0
+    mat = sp.hstack([sp.identity(n_rows, dtype=np.float32, format="csr"), tags]).tocsr() \
+        if identity else tags
+    if normalize:
+        s = np.asarray(mat.sum(axis=1)).ravel()
+        s[s == 0] = 1.0
+        mat = sp.diags((1.0 / s).astype(np.float32)).dot(mat).tocsr()
+    mat = mat.astype(np.float32)
+    mat.sort_indices()
+    return mat
+
+
+def init_arrays(random_state, n_item_features, n_user_features, d, schedule="adagrad"):
+    """Model initialisation, same RNG consumption order as lightfm.py:281-312."""
+    a = {}
+    a["item_embeddings"] = ((random_state.rand(n_item_features, d) - 0.5) / d).astype(np.float32)
+    a["item_embedding_gradients"] = np.zeros_like(a["item_embeddings"])
+    a["item_embedding_momentum"] = np.zeros_like(a["item_embeddings"])
+    a["item_biases"] = np.zeros(n_item_features, dtype=np.float32)
+    a["item_bias_gradients"] = np.zeros_like(a["item_biases"])
+    a["item_bias_momentum"] = np.zeros_like(a["item_biases"])
+    a["user_embeddings"] = ((random_state.rand(n_user_features, d) - 0.5) / d).astype(np.float32)
+    a["user_embedding_gradients"] = np.zeros_like(a["user_embeddings"])
+    a["user_embedding_momentum"] = np.zeros_like(a["user_embeddings"])
+    a["user_biases"] = np.zeros(n_user_features, dtype=np.float32)
+    a["user_bias_gradients"] = np.zeros_like(a["user_biases"])
+    a["user_bias_momentum"] = np.zeros_like(a["user_biases"])
+    if schedule == "adagrad":
+        for k in ("item_embedding_gradients", "item_bias_gradients",
+                  "user_embedding_gradients", "user_bias_gradients"):
+            a[k] += 1
+    return a
+
+
+def copy_arrays(a):
+    return {k: v.copy() for k, v in a.items()}
+
+
+class Hyper(object):
+    def __init__(self, d=16, schedule="adagrad", lr=0.05, rho=0.95, eps=1e-6, max_sampled=10,
+                 item_alpha=0.0, user_alpha=0.0, k=5, n=10):
+        self.d, self.schedule, self.lr, self.rho, self.eps = d, schedule, lr, rho, eps
+        self.max_sampled, self.item_alpha, self.user_alpha = max_sampled, item_alpha, user_alpha
+        self.k, self.n = k, n
+
+
+def holder(api, arrays, hp):
+    return api.FastLightFM(*[arrays[k] for k in MODEL_ARRAYS], hp.d,
+                           int(hp.schedule == "adadelta"), hp.lr, hp.rho, hp.eps, hp.max_sampled)
+
+
+def run_epoch(api, loss, interactions, arrays, hp, random_state, item_features=None,
+              user_features=None, sample_weight=None, num_threads=1):
+    """One epoch exactly as lightfm.py:668-759 drives the native module."""
+    inter = interactions.tocoo()
+    n_users, n_items = inter.shape
+    itf = item_features if item_features is not None else \
+        sp.identity(n_items, dtype=np.float32, format="csr")
+    usf = user_features if user_features is not None else \
+        sp.identity(n_users, dtype=np.float32, format="csr")
+    sw = sample_weight if sample_weight is not None else \
+        (inter.data if np.array_equiv(inter.data, 1.0) else np.ones_like(inter.data))
+    if loss in ("warp", "bpr", "warp-kos"):
+        lookup = inter.tocsr()
+        if not lookup.has_sorted_indices:
+            lookup = lookup.sorted_indices()
+        positives = api.CSRMatrix(lookup)
+    shuffle = np.arange(len(inter.data), dtype=np.int32)
+    random_state.shuffle(shuffle)
+    h = holder(api, arrays, hp)
+    ci, cu = api.CSRMatrix(itf), api.CSRMatrix(usf)
+    if loss == "warp":
+        api.fit_warp(ci, cu, positives, inter.row, inter.col, inter.data, sw, shuffle, h, hp.lr,
+                     hp.item_alpha, hp.user_alpha, num_threads, random_state)
+    elif loss == "bpr":
+        api.fit_bpr(ci, cu, positives, inter.row, inter.col, inter.data, sw, shuffle, h, hp.lr,
+                    hp.item_alpha, hp.user_alpha, num_threads, random_state)
+    elif loss == "warp-kos":
+        api.fit_warp_kos(ci, cu, positives, inter.row, shuffle, h, hp.lr, hp.item_alpha,
+                         hp.user_alpha, hp.k, hp.n, num_threads, random_state)
+    else:
+        api.fit_logistic(ci, cu, inter.row, inter.col, inter.data, sw, shuffle, h, hp.lr,
+                         hp.item_alpha, hp.user_alpha, num_threads)
+
+
+def reference_native(variant="strict"):
+    """Namespace over the REAL reference's native module (oracle/_ref)."""
+    import oracle
+    ref = oracle.load_reference(variant)
+    import lightfm._lightfm_fast as fast
+    return types.SimpleNamespace(
+        CSRMatrix=fast.CSRMatrix, FastLightFM=fast.FastLightFM, fit_warp=fast.fit_warp,
+        fit_bpr=fast.fit_bpr, fit_warp_kos=fast.fit_warp_kos, fit_logistic=fast.fit_logistic,
+        predict_lightfm=fast.predict_lightfm, predict_ranks=fast.predict_ranks,
+        calculate_auc_from_rank=fast.calculate_auc_from_rank,
+        test_in_positives=fast.__test_in_positives, package=ref)
+
+
+def oracle_native():
+    import oracle
+    return oracle
+
+
+def cuda_native():
+    from lightfm_b200 import _lightfm_fast as fast
+    return types.SimpleNamespace(
+        CSRMatrix=fast.CSRMatrix, FastLightFM=fast.FastLightFM, fit_warp=fast.fit_warp,
+        fit_bpr=fast.fit_bpr, fit_warp_kos=fast.fit_warp_kos, fit_logistic=fast.fit_logistic,
+        predict_lightfm=fast.predict_lightfm, predict_ranks=fast.predict_ranks,
+        calculate_auc_from_rank=fast.calculate_auc_from_rank,
+        test_in_positives=getattr(fast, "__test_in_positives"), module=fast)
+
+
+def max_rel_diff(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-12))) if a.size else 0.0

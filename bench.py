@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE.json's config.
+
+metric  : positive interactions/sec per epoch (WARP, 64 components)
+workload: C2 = MovieLens-20M-shaped synthetic (138 493 x 26 744, 20 M nnz), identity
+          features, WARP, d=64, max_sampled=10, adagrad lr 0.05  (BASELINE.json configs[1])
+step    : one epoch = one pass of fit_warp over the 20 M interactions
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+`value`  kernels only, inputs resident in HBM (lfm_plan_epoch: pack + SGD kernel), CUDA events
+`e2e`    the drop-in boundary call `_lightfm_fast.fit_warp(...)` with HOST (pinned) buffers:
+         every step copies all inputs + the model to the device and the model back
+`roofline` algorithmic bytes (SURVEY 8(d) formula x the run's own counters) / SGD-kernel time
+`cpu_baseline` the reference's own OpenMP fit_warp (oracle/_ref) on this box's host cores,
+         bounded sample of the same workload (rank 0, N=1)
+
+--impl reference times the unmodified reference (oracle/_ref, rebuilt -march=native for this
+host) through the same boundary call on a bounded sample per step.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+import scipy.sparse as sp
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "positive interactions/sec per epoch (WARP, 64 comp)"
+UNIT = "interactions/s"
+WORKLOAD = "C2: ML-20M-shaped synthetic 138493x26744, 20M nnz, identity features, WARP, d=64, max_sampled=10"
+N_USERS, N_ITEMS, NNZ, D = 138_493, 26_744, 20_000_000, 64
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ---- data ---------------------------------------------------------------------------------
+def gen_interactions(n_users, n_items, nnz, seed, device):
+    """Same distribution as lightfm_b200.synthetic.interactions, generated with torch on
+    `device` (20 M unique keys take ~70 s in numpy, ~1 s on the GPU)."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    keys = torch.empty(0, dtype=torch.int64, device=device)
+    draw = int(nnz * 1.25) + 16
+    while keys.numel() < nnz:
+        u = torch.floor(n_users * torch.rand(draw, generator=g, device=device, dtype=torch.float64) ** 1.5).long()
+        i = torch.floor(n_items * torch.rand(draw, generator=g, device=device, dtype=torch.float64) ** 2.0).long()
+        keys = torch.unique(torch.cat([keys, u * n_items + i]))
+        draw = max(int((nnz - keys.numel()) * 2.0) + 16, 1024)
+    perm = torch.randperm(keys.numel(), generator=g, device=device)[:nnz]
+    keys = keys[perm]
+    rows = (keys // n_items).to(torch.int32).cpu().numpy()
+    cols = (keys % n_items).to(torch.int32).cpu().numpy()
+    return rows, cols
+
+
+def pinned(arr):
+    """Copy a numpy array into page-locked host memory (numpy view of a pinned torch tensor)."""
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(arr))
+    if torch.cuda.is_available():
+        t = t.pin_memory()
+    return t.numpy(), t
+
+
+class Problem(object):
+    def __init__(self, n_users, n_items, nnz, d, seed, device, pin=True):
+        self.keep = []
+        rows, cols = gen_interactions(n_users, n_items, nnz, seed, device)
+        data = np.ones(len(rows), dtype=np.float32)
+        csr = sp.csr_matrix((data, (rows, cols)), shape=(n_users, n_items))
+        csr.sort_indices()
+        self.n_users, self.n_items, self.nnz, self.d = n_users, n_items, len(rows), d
+        P = self._pin if pin else (lambda a: np.ascontiguousarray(a))
+        self.row, self.col, self.data = P(rows), P(cols), P(data)
+        self.pos = sp.csr_matrix((P(csr.data), P(csr.indices.astype(np.int32)),
+                                  P(csr.indptr.astype(np.int32))), shape=csr.shape)
+        self.itf = sp.identity(n_items, dtype=np.float32, format="csr")
+        self.usf = sp.identity(n_users, dtype=np.float32, format="csr")
+        for m in (self.itf, self.usf):
+            m.indices = P(m.indices.astype(np.int32))
+            m.indptr = P(m.indptr.astype(np.int32))
+            m.data = P(m.data)
+        rs = np.random.RandomState(seed)
+        self.state = {}
+        for side, n in (("item", n_items), ("user", n_users)):
+            emb = ((rs.rand(n, d) - 0.5) / d).astype(np.float32)
+            self.state[side + "_w"] = P(emb)
+            self.state[side + "_g"] = P(np.ones_like(emb))
+            self.state[side + "_m"] = P(np.zeros_like(emb))
+            self.state[side + "_b"] = P(np.zeros(n, np.float32))
+            self.state[side + "_bg"] = P(np.ones(n, np.float32))
+            self.state[side + "_bm"] = P(np.zeros(n, np.float32))
+        self.shuffle = P(np.arange(self.nnz, dtype=np.int32))
+
+    def _pin(self, a):
+        v, t = pinned(a)
+        self.keep.append(t)
+        return v
+
+    def holder(self, api, lr=0.05, max_sampled=10):
+        s = self.state
+        return api.FastLightFM(s["item_w"], s["item_g"], s["item_m"], s["item_b"], s["item_bg"],
+                               s["item_bm"], s["user_w"], s["user_g"], s["user_m"], s["user_b"],
+                               s["user_bg"], s["user_bm"], self.d, 0, lr, 0.95, 1e-6, max_sampled)
+
+
+def algorithmic_bytes(c, d, f_user=1, f_item=1):
+    """bytes one epoch must move, from the run's own counters (identity features)."""
+    R = 4 * d + 4
+    gather = lambda f: 8 + f * (8 + R)
+    P, S, U = c["positives"], c["negatives_drawn"], c["updates"]
+    fwd = P * (20 + gather(f_user) + gather(f_item)) + S * gather(f_item) + U * (8 + 4 * 8)
+    upd = U * (f_user + 2 * f_item) * 3 * R
+    return float(fwd + upd)
+
+
+# ---- clocks -----------------------------------------------------------------------------------
+class ClockSampler(object):
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(prefix="lfm_clocks_", suffix=".csv")
+        self.proc = None
+        self.gpu = gpu_index
+        self.t0 = self.t1 = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=timestamp," + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def mark(self, begin):
+        if begin:
+            self.t0 = time.time()
+        else:
+            self.t1 = time.time()
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        import datetime
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 10:
+                continue
+            try:
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except Exception:
+                ts = None
+            if ts is not None and self.t0 and self.t1 and not (self.t0 - 0.05 <= ts <= self.t1 + 0.05):
+                continue
+            try:
+                sm.append(float(parts[2]))
+                mx.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                  "sw_power_cap"), parts[6:10]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ---- reference (CPU) ------------------------------------------------------------------------------
+def load_reference_native():
+    """The unmodified reference, recompiled with its shipped flags for THIS host's CPU."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import build_ref
+    variant_dir = build_ref.rebuild_native()
+    sys.path.insert(0, variant_dir)
+    import lightfm._lightfm_fast as fast  # noqa
+    kind = os.path.basename(variant_dir)
+    return fast, kind
+
+
+def reference_epoch(fast, prob, sample, threads, rs):
+    """One fit_warp call of the reference on the first `sample` interactions."""
+    n = sample
+    row, col, data = prob.row[:n], prob.col[:n], prob.data[:n]
+    pos = sp.csr_matrix((data, (row, col)), shape=(prob.n_users, prob.n_items))
+    pos.sort_indices()
+    pos.indices = pos.indices.astype(np.int32)
+    pos.indptr = pos.indptr.astype(np.int32)
+    shuffle = np.arange(n, dtype=np.int32)
+    rs.shuffle(shuffle)
+    h = prob.holder(fast)
+    t0 = time.perf_counter()
+    fast.fit_warp(fast.CSRMatrix(prob.itf), fast.CSRMatrix(prob.usf), fast.CSRMatrix(pos), row, col,
+                  data, data, shuffle, h, 0.05, 0.0, 0.0, threads, rs)
+    return time.perf_counter() - t0
+
+
+def calibrate_reference(fast, prob, threads, target_s):
+    rs = np.random.RandomState(0)
+    probe = min(prob.nnz, 400_000)
+    reference_epoch(fast, prob, min(prob.nnz, 100_000), threads, rs)  # warm caches / page in
+    dt = reference_epoch(fast, prob, probe, threads, rs)
+    rate = probe / dt
+    sample = int(min(prob.nnz, max(probe, rate * target_s)))
+    return sample, rate
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    try:
+        fast, kind = load_reference_native()
+    except Exception as exc:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref missing or unbuildable: %s" % exc}))
+        return
+    import torch
+    device = "cuda" if torch.cuda.is_available() else "cpu"
+    prob = Problem(N_USERS, N_ITEMS, args.nnz, D, seed=2, device=device, pin=False)
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    sample, _ = calibrate_reference(fast, prob, threads, target_s=min(8.0, max(1.0, budget)))
+    rs = np.random.RandomState(1)
+    for _ in range(args.warmup):
+        reference_epoch(fast, prob, sample, threads, rs)
+    times = [reference_epoch(fast, prob, sample, threads, rs) for _ in range(args.steps)]
+    total = sum(times)
+    value = sample * args.steps / total
+    desc = "first %d of the %d shuffled interactions per step, full 138493x26744 tables" % (sample, prob.nnz)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "sample": desc,
+                                        "reference_build": kind + " (-O3 -ffast-math -march=native -fopenmp)"
+                                        if kind == "native" else kind},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ---- our arm ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from lightfm_b200 import _lightfm_fast as fast
+    fast._lib.lfm_set_device(local)
+    fast.set_mode("hogwild")
+
+    if world > 1:
+        import bench_multigpu
+        return bench_multigpu.run(args, rank, world, local)
+
+    t_gen = time.time()
+    prob = Problem(N_USERS, N_ITEMS, args.nnz, D, seed=2, device="cuda")
+    log("data generated in %.1fs (nnz=%d)" % (time.time() - t_gen, prob.nnz))
+    itf, usf, pos = fast.CSRMatrix(prob.itf), fast.CSRMatrix(prob.usf), fast.CSRMatrix(prob.pos)
+    holder = prob.holder(fast)
+    threads = max(2, os.cpu_count() or 2)
+
+    clocks = ClockSampler(local)
+    clocks.start()
+
+    # -- value: resident plan, kernels only --------------------------------------------------
+    plan = fast.ResidentPlan("warp", itf, usf, pos, prob.row, prob.col, prob.data, prob.data,
+                             holder, 0.0, 0.0)
+    for w in range(args.warmup):
+        plan.epoch(seed=1000 + w, num_threads=threads)
+    torch.cuda.synchronize()
+    clocks.mark(True)
+    t0 = time.perf_counter()
+    counters = [plan.epoch(seed=2000 + s, num_threads=threads) for s in range(args.steps)]
+    torch.cuda.synchronize()
+    wall_resident = time.perf_counter() - t0
+    clocks.mark(False)
+    clk = clocks.stop()
+    plan.download()
+    plan.close()
+    positives = sum(c["positives"] for c in counters)
+    dev_ms = sum(c["kernel_ms"] for c in counters)
+    train_ms = sum(c["train_kernel_ms"] for c in counters)
+    launches = sum(c["kernel_launches"] for c in counters)
+    value = positives / (dev_ms / 1e3)
+    abytes = sum(algorithmic_bytes(c, D) for c in counters)
+    achieved = abytes / (train_ms / 1e3) / 1e9
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback"
+
+    # -- e2e: the boundary call with host buffers ----------------------------------------------
+    rs = np.random.RandomState(5)
+    e2e_times, e2e_pos, h2d, d2h = [], 0, 0, 0
+    for s in range(args.warmup + args.steps):
+        rs.shuffle(prob.shuffle)  # outside the timed call, as lightfm.py does it before the call
+        t0 = time.perf_counter()
+        fast.fit_warp(itf, usf, pos, prob.row, prob.col, prob.data, prob.data, prob.shuffle, holder,
+                      0.05, 0.0, 0.0, threads, rs)
+        dt = time.perf_counter() - t0
+        c = fast.last_counters["fit"]
+        if s >= args.warmup:
+            e2e_times.append(dt)
+            e2e_pos += c["positives"]
+            h2d, d2h = c["h2d_bytes"], c["d2h_bytes"]
+            launches += c["kernel_launches"]
+    e2e_value = e2e_pos / sum(e2e_times)
+    finite = all(np.isfinite(v).all() for v in prob.state.values())
+
+    # -- cpu baseline: the reference's OpenMP fit_warp on this host ------------------------------
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            ref_fast, kind = load_reference_native()
+            cores = os.cpu_count() or 1
+            cpu_prob = prob
+            sample, _ = calibrate_reference(ref_fast, cpu_prob, cores, target_s=12.0)
+            dt = reference_epoch(ref_fast, cpu_prob, sample, cores, np.random.RandomState(3))
+            cpu = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "reference",
+                   "sample": "one fit_warp call on the first %d of %d shuffled interactions, %d OpenMP "
+                             "threads, build=%s" % (sample, prob.nnz, cores, kind)}
+        except Exception as exc:  # pragma: no cover
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
+                   "sample": "unavailable: %s" % exc}
+
+    mean = lambda k: sum(c[k] for c in counters) / len(counters)
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "nnz": prob.nnz, "mode": "hogwild",
+                   "l2": "inputs (tuples 320 MB + tables 85 MB + CSR 80 MB) exceed the 126 MB L2",
+                   "wall_ms_per_step_resident": 1e3 * wall_resident / args.steps,
+                   "negatives_per_positive": mean("negatives_drawn") / mean("positives"),
+                   "updates_per_positive": mean("updates") / mean("positives"),
+                   "weights_finite": bool(finite)},
+        "clocks": clk,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1e3 * sum(e2e_times) / len(e2e_times),
+                "call": "lightfm_b200._lightfm_fast.fit_warp(host pinned buffers)"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "kernel": "fast_rank_kernel<WARP,16>", "kernel_ms": train_ms / args.steps,
+                     "algorithmic_bytes_per_step": abytes / args.steps},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
+    ap.add_argument("--nnz", type=int, default=NNZ, help="debug: smaller interaction count")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

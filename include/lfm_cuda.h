@@ -101,7 +101,8 @@ typedef struct {
     int64_t negatives_drawn;  /* S_total: negative items scored                       */
     int64_t updates;          /* U_total: gradient steps applied                      */
     int64_t rejected;         /* violating draws discarded because in_positives       */
-    double kernel_ms;         /* device time of the training kernel(s), CUDA events   */
+    double kernel_ms;         /* device time of all kernels of the call (pack + train + regularize) */
+    double train_kernel_ms;   /* device time of the SGD kernel(s) alone (roofline denominator)      */
     double h2d_ms, d2h_ms;    /* copy time inside the call                            */
     int64_t h2d_bytes, d2h_bytes;
     int32_t kernel_launches;  /* kernels of this library launched by the call         */
@@ -180,6 +181,25 @@ int lfm_calculate_auc_from_rank(const lfm_csr *ranks, const int32_t *num_train_p
 
 /* T:1380-1385 (test hook; runs the device membership search). Returns 0/1, <0 on error. */
 int lfm_test_in_positives(int32_t row, int32_t col, const lfm_csr *mat);
+
+/* ---- resident plans (epoch prep of lightfm.py:668-759) ------------
+ * The reference re-wraps and re-walks every input once per epoch.  A plan uploads the
+ * interactions, feature matrices, positives lookup and model state once, runs epochs
+ * on the device and copies the model back on request.  `loss`: 0 logistic, 1 warp,
+ * 2 bpr, 3 warp-kos.  `interactions` is the sorted positives CSR (NULL for logistic);
+ * item_ids / Y / sample_weight are NULL for warp-kos.                                  */
+typedef struct lfm_plan lfm_plan;
+int lfm_plan_create(lfm_plan **out, int32_t loss, const lfm_csr *item_features,
+                    const lfm_csr *user_features, const lfm_csr *interactions,
+                    const int32_t *user_ids, const int32_t *item_ids, const float *Y,
+                    const float *sample_weight, int64_t no_examples, const lfm_model *model,
+                    double item_alpha, double user_alpha, int32_t k, int32_t n);
+/* One epoch.  shuffle_indices == NULL (hogwild only): a fresh device-generated
+ * permutation keyed by `seed` replaces the host shuffle of lightfm.py:689-690. */
+int lfm_plan_epoch(lfm_plan *plan, const int32_t *shuffle_indices, uint32_t seed,
+                   int32_t num_threads, lfm_counters *counters);
+int lfm_plan_download(lfm_plan *plan, lfm_model *model);
+int lfm_plan_destroy(lfm_plan *plan);
 
 #ifdef __cplusplus
 }

@@ -57,6 +57,7 @@ class LfmCounters(C.Structure):
         ("updates", C.c_int64),
         ("rejected", C.c_int64),
         ("kernel_ms", C.c_double),
+        ("train_kernel_ms", C.c_double),
         ("h2d_ms", C.c_double),
         ("d2h_ms", C.c_double),
         ("h2d_bytes", C.c_int64),
@@ -100,6 +101,12 @@ LIB_ONLY = {
     "lfm_set_mode": (C.c_int, [C.c_int]),
     "lfm_get_mode": (C.c_int, []),
     "lfm_release_cache": (C.c_int, []),
+    "lfm_plan_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, CsrP, CsrP, CsrP, c_i32p, c_i32p,
+                                  c_f32p, c_f32p, C.c_int64, ModelP, C.c_double, C.c_double,
+                                  C.c_int32, C.c_int32]),
+    "lfm_plan_epoch": (C.c_int, [C.c_void_p, c_i32p, C.c_uint32, C.c_int32, CountersP]),
+    "lfm_plan_download": (C.c_int, [C.c_void_p, ModelP]),
+    "lfm_plan_destroy": (C.c_int, [C.c_void_p]),
 }
 
 

@@ -1,0 +1,140 @@
+"""Drop-in replacement for the reference's ``lightfm/_lightfm_fast.py`` import shim.
+
+The reference module re-exports the names of its Cython extension
+(``/root/reference/lightfm/_lightfm_fast.py:1-15``).  This one exports the same
+ten names -- ``CSRMatrix, FastLightFM, fit_logistic, fit_warp, fit_warp_kos,
+fit_bpr, predict_lightfm, predict_ranks, calculate_auc_from_rank,
+__test_in_positives`` -- bound with ctypes to ``libfm_cuda.so`` (C ABI in
+``include/lfm_cuda.h``), whose kernels are hand-written CUDA for sm_100a.
+
+There is no CPU fallback: if the shared library is missing the import fails, and
+if no CUDA device is usable every compute call raises ``RuntimeError``.
+
+Execution mode (``num_threads`` has no natural meaning on a GPU):
+  ``num_threads == 1``  deterministic replay of the reference's single-thread order
+  ``num_threads  > 1``  hogwild throughput mode (one warp per interaction)
+override with ``LIGHTFM_CUDA_MODE=replay|hogwild|auto`` or :func:`set_mode`.
+"""
+import ctypes
+import os
+
+from . import _abi
+from ._abi import CSRMatrix, FastLightFM  # noqa: F401  (re-exported)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.environ.get("LIGHTFM_CUDA_LIB", os.path.join(_HERE, "csrc", "libfm_cuda.so"))
+
+if not os.path.exists(_LIB_PATH):
+    raise ImportError(
+        "libfm_cuda.so not found at %s. Build it with `python -m lightfm_b200._build` "
+        "(needs nvcc). lightfm_b200 has no CPU fallback." % _LIB_PATH)
+
+_lib = _abi.bind(ctypes.CDLL(_LIB_PATH), prefix="lfm_")
+LIBRARY_PATH = _LIB_PATH
+
+
+def _check(status):
+    if status == 0:
+        return
+    msg = (_lib.lfm_last_error() or b"").decode("utf-8", "replace")
+    if status == -1:
+        raise ValueError(msg)
+    if status == -3:
+        raise MemoryError(msg)
+    raise RuntimeError("libfm_cuda: %s (status %d)" % (msg, status))
+
+
+_MODES = {"auto": 0, "replay": 1, "hogwild": 2}
+
+
+def set_mode(mode):
+    """'auto' (num_threads==1 -> replay, >1 -> hogwild), 'replay' or 'hogwild'."""
+    _check(_lib.lfm_set_mode(_MODES[mode]))
+
+
+def get_mode():
+    return {v: k for k, v in _MODES.items()}[_lib.lfm_get_mode()]
+
+
+def device_count():
+    return _lib.lfm_device_count()
+
+
+def set_fast_path(enabled):
+    """Testing hook: disable the specialised hogwild kernels (generic ones run instead)."""
+    fn = _lib.lfm_set_fast_path
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_int]
+    return fn(int(bool(enabled)))
+
+
+def release_cache():
+    _check(_lib.lfm_release_cache())
+
+
+if os.environ.get("LIGHTFM_CUDA_MODE"):
+    set_mode(os.environ["LIGHTFM_CUDA_MODE"].lower())
+
+_api = _abi.make_api(_lib, "lfm_", _check)
+fit_logistic = _api["fit_logistic"]
+fit_warp = _api["fit_warp"]
+fit_bpr = _api["fit_bpr"]
+fit_warp_kos = _api["fit_warp_kos"]
+predict_lightfm = _api["predict_lightfm"]
+predict_ranks = _api["predict_ranks"]
+calculate_auc_from_rank = _api["calculate_auc_from_rank"]
+globals()["__test_in_positives"] = _api["__test_in_positives"]
+# Work counters of the most recent fit_* call (negatives drawn, updates, device ms, bytes).
+last_counters = _api["last_counters"]
+
+__all__ = ["CSRMatrix", "FastLightFM", "fit_logistic", "fit_warp", "fit_bpr", "fit_warp_kos",
+           "predict_lightfm", "predict_ranks", "calculate_auc_from_rank"]
+
+
+_LOSS_CODES = {"logistic": 0, "warp": 1, "bpr": 2, "warp-kos": 3}
+
+
+class ResidentPlan(object):
+    """One training problem kept in HBM across epochs (``lfm_plan_*`` in lfm_cuda.h).
+
+    Uploads the interactions, feature matrices, positives lookup and the model once;
+    ``epoch()`` then runs entirely on the device; ``download()`` writes the model back
+    into the numpy arrays of the ``FastLightFM`` it was created from.
+    """
+
+    def __init__(self, loss, item_features, user_features, interactions, user_ids, item_ids, Y,
+                 sample_weight, lightfm, item_alpha, user_alpha, k=5, n=10):
+        self._handle = ctypes.c_void_p()
+        self._lightfm = lightfm
+        self._keep = (item_features, user_features, interactions, user_ids, item_ids, Y, sample_weight)
+        n_ex = len(user_ids)
+        null_i = ctypes.cast(None, _abi.c_i32p)
+        null_f = ctypes.cast(None, _abi.c_f32p)
+        _check(_lib.lfm_plan_create(
+            ctypes.byref(self._handle), _LOSS_CODES[loss], item_features.ptr, user_features.ptr,
+            interactions.ptr if interactions is not None else None,
+            _abi.i32p(user_ids), _abi.i32p(item_ids) if item_ids is not None else null_i,
+            _abi.f32p(Y) if Y is not None else null_f,
+            _abi.f32p(sample_weight) if sample_weight is not None else null_f,
+            n_ex, lightfm.ptr, float(item_alpha), float(user_alpha), int(k), int(n)))
+
+    def epoch(self, seed, num_threads=2, shuffle_indices=None):
+        cnt = _abi.LfmCounters()
+        sh = _abi.i32p(shuffle_indices) if shuffle_indices is not None else ctypes.cast(None, _abi.c_i32p)
+        _check(_lib.lfm_plan_epoch(self._handle, sh, int(seed) & 0xFFFFFFFF, int(num_threads),
+                                   ctypes.byref(cnt)))
+        return cnt.as_dict()
+
+    def download(self):
+        _check(_lib.lfm_plan_download(self._handle, self._lightfm.ptr))
+
+    def close(self):
+        if self._handle:
+            _lib.lfm_plan_destroy(self._handle)
+            self._handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,484 @@
+// lfm_hogwild.cu -- throughput mode (num_threads > 1): one warp per interaction,
+// lock-free concurrent updates over the whole GPU.
+//
+// The reference runs the SGD loop under an OpenMP prange with racy, lock-free
+// read-modify-writes on the shared tables (Hogwild; T:825 and SURVEY 0).  Here
+// every warp takes one (user, positive item) tuple:
+//   gather user / item rows (coalesced, L2-coherent ld.global.cg) -> registers
+//   warp-shuffle dot product
+//   Philox4x32 negative draws, WARP rank-sampling loop in registers
+//   Adagrad-scaled deltas scattered with red.global.add (no lost updates)
+// Floating point is fp32 with FMA; results are statistically equivalent to the
+// reference's multi-thread runs, not bit-equal (nor is the reference to itself).
+//
+// Two kernel families:
+//   generic   lanes own components l, l+32, ...; any d <= 256, any feature CSR,
+//             adagrad / adadelta, L2 regularisation.
+//   fast      identity features, adagrad, alpha == 0, d in {16, 32, 64, 128}:
+//             float4 lanes, several rows per load instruction, speculative
+//             negative batches, vector red.global.add.v4.f32 (lfm_hogwild_fast.cuh).
+//
+// Reference: fit_logistic T:694-781, fit_warp T:784-912, fit_warp_kos T:915-1071,
+// fit_bpr T:1074-1182, update T:454-534, warp_update T:537-649.
+#include "lfm_common.cuh"
+
+namespace {
+
+// ---- device-side permutation (used when no host shuffle is supplied) ---------
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+// 4-round Feistel network on 2*hb bits + cycle walking: a bijection of [0, n).
+__device__ __forceinline__ int64_t feistel_perm(int64_t i, int64_t n, int hb, uint32_t key) {
+    uint32_t mask = (1u << hb) - 1u;
+    uint64_t x = (uint64_t)i;
+    do {
+        uint32_t l = (uint32_t)(x >> hb) & mask, r = (uint32_t)x & mask;
+#pragma unroll
+        for (int round = 0; round < 4; round++) {
+            uint32_t f = mix32(r ^ (key + 0x9E3779B9u * (round + 1))) & mask;
+            uint32_t t = l ^ f;
+            l = r;
+            r = t;
+        }
+        x = ((uint64_t)l << hb) | r;
+    } while (x >= (uint64_t)n);
+    return (int64_t)x;
+}
+
+__global__ void pack_kernel(const int32_t* __restrict__ user_ids, const int32_t* __restrict__ item_ids,
+                            const float* __restrict__ y, const float* __restrict__ w,
+                            const int32_t* __restrict__ shuffle, int64_t n, int hb, uint32_t key,
+                            int skip_nonpositive, Tuple* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        int64_t row = shuffle ? (int64_t)shuffle[i] : feistel_perm(i, n, hb, key);
+        Tuple t;
+        t.user = user_ids[row];
+        t.item = item_ids ? item_ids[row] : 0;
+        t.y = y ? y[row] : 1.0f;
+        t.weight = w ? w[row] : 1.0f;
+        if (skip_nonpositive && !(t.y > 0)) t.user = -1;
+        out[i] = t;
+    }
+}
+
+// ---- generic kernel ------------------------------------------------------------
+template <int KPL>
+struct Repr {
+    float v[KPL];
+    float b;
+};
+
+// Gather one entity's representation: lanes own components lane + 32*k.
+template <int KPL>
+__device__ __forceinline__ void gather(const DevCsr& f, const DevTable& t, int d, int row,
+                                       float scale, Repr<KPL>& r, int lane) {
+#pragma unroll
+    for (int k = 0; k < KPL; k++) r.v[k] = 0.0f;
+    r.b = 0.0f;
+    if (f.identity) {
+        const float* p = t.w + (size_t)row * d;
+#pragma unroll
+        for (int k = 0; k < KPL; k++) {
+            int c = lane + 32 * k;
+            if (c < d) r.v[k] = scale * __ldcg(p + c);
+        }
+        r.b = scale * __ldcg(t.b + row);
+        return;
+    }
+    int start = __ldg(f.indptr + row), stop = __ldg(f.indptr + row + 1);
+    for (int i = start; i < stop; i++) {
+        int ft = __ldg(f.indices + i);
+        float fw = __ldg(f.data + i) * scale;
+        const float* p = t.w + (size_t)ft * d;
+#pragma unroll
+        for (int k = 0; k < KPL; k++) {
+            int c = lane + 32 * k;
+            if (c < d) r.v[k] = fmaf(fw, __ldcg(p + c), r.v[k]);
+        }
+        r.b = fmaf(fw, __ldcg(t.b + ft), r.b);
+    }
+}
+
+template <int KPL>
+__device__ __forceinline__ float dot(const Repr<KPL>& a, const Repr<KPL>& b) {
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < KPL; k++) s = fmaf(a.v[k], b.v[k], s);  // lanes past d hold zeros
+    return lfm_warp_sum(s) + a.b + b.b;
+}
+
+// One parameter step in hogwild arithmetic.  Adagrad: pure adds -> red.global.add.
+// Adadelta: not expressible as adds -> racy plain RMW, as in the reference.
+// Returns the local learning rate (for the lazy-regularisation average).
+template <bool ADADELTA>
+__device__ __forceinline__ float hstep(float* w, float* G, float* M, float fw, float grad,
+                                       const DevModel& m, float alpha) {
+    float llr;
+    if (ADADELTA) {
+        float g0 = __ldcg(G), m0 = __ldcg(M), w0 = __ldcg(w);
+        float t = fw * grad;
+        float g1 = m.rho * g0 + (1.0f - m.rho) * t * t;
+        llr = sqrtf(m0 + m.eps) / sqrtf(g1 + m.eps);
+        float upd = llr * grad * fw;
+        float m1 = m.rho * m0 + (1.0f - m.rho) * upd * upd;
+        float w1 = (w0 - upd) * (1.0f + alpha * llr);
+        __stcg(G, g1);
+        __stcg(M, m1);
+        __stcg(w, w1);
+    } else {
+        float g0 = __ldcg(G);
+        llr = m.lr * rsqrtf(g0);
+        float gw = grad * fw;
+        float delta = -llr * gw;
+        if (alpha != 0.0f) {
+            float w0 = __ldcg(w);
+            delta += (w0 + delta) * (alpha * llr);
+        }
+        atomicAdd(w, delta);
+        atomicAdd(G, gw * gw);
+    }
+    return llr;
+}
+
+// Apply `grad[k]` (per owned component) and `bgrad` to every feature row of `row`.
+template <int KPL, bool ADADELTA>
+__device__ __forceinline__ float scatter(const DevCsr& f, DevTable& t, const DevModel& m, int row,
+                                         const float (&grad)[KPL], float bgrad, float alpha,
+                                         int lane, int& nnz) {
+    float lrsum = 0.0f;
+    int d = m.d;
+    int start, stop;
+    if (f.identity) { start = row; stop = row + 1; }
+    else { start = __ldg(f.indptr + row); stop = __ldg(f.indptr + row + 1); }
+    nnz = stop - start;
+    for (int i = start; i < stop; i++) {
+        int ft = f.identity ? row : __ldg(f.indices + i);
+        float fw = f.identity ? 1.0f : __ldg(f.data + i);
+        size_t o = (size_t)ft * d;
+#pragma unroll
+        for (int k = 0; k < KPL; k++) {
+            int c = lane + 32 * k;
+            if (c < d)
+                lrsum += hstep<ADADELTA>(t.w + o + c, t.g + o + c, ADADELTA ? t.m + o + c : nullptr,
+                                         fw, grad[k], m, alpha);
+        }
+        if (lane == 0)
+            lrsum += hstep<ADADELTA>(t.b + ft, t.bg + ft, ADADELTA ? t.bm + ft : nullptr, fw, bgrad,
+                                     m, alpha);
+    }
+    return lrsum;
+}
+
+struct RegState {  // per-warp view of the lazy-regularisation scales (log domain)
+    double base_i, base_u;  // last value read from global
+    double loc_i, loc_u;    // local contribution not yet flushed
+    int pending;
+};
+
+template <int LOSS, int KPL, bool ADADELTA, bool REG>
+__global__ void __launch_bounds__(256) hogwild_kernel(FitArgs a, const Tuple* __restrict__ tuples) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    DevModel& m = a.model;
+    const int d = m.d;
+    const float alpha_i = (float)a.item_alpha, alpha_u = (float)a.user_alpha;
+    const int n_items = a.itf.rows;
+    unsigned long long c_pos = 0, c_neg = 0, c_upd = 0, c_rej = 0;
+
+    RegState rs;
+    rs.base_i = rs.base_u = rs.loc_i = rs.loc_u = 0.0;
+    rs.pending = 0;
+    if (REG) {
+        rs.base_i = __ldcg(&a.scales->item_scale);  // log-scale in hogwild mode
+        rs.base_u = __ldcg(&a.scales->user_scale);
+    }
+
+    for (int64_t t = warp; t < a.n; t += nwarps) {
+        Tuple tp = tuples[t];
+        if (tp.user < 0) continue;
+        float item_scale = 1.0f, user_scale = 1.0f;
+        if (REG) {
+            item_scale = (float)exp(rs.base_i + rs.loc_i);
+            user_scale = (float)exp(rs.base_u + rs.loc_u);
+        }
+        const int user = tp.user;
+        Repr<KPL> u, p, q;
+        gather<KPL>(a.usf, m.user, d, user, user_scale, u, lane);
+        float lrsum = 0.0f;
+        int nnz_total = 0;
+        bool updated = false;
+
+        if (LOSS == LOSS_LOGISTIC) {
+            gather<KPL>(a.itf, m.item, d, tp.item, item_scale, p, lane);
+            float pred = 1.0f / (1.0f + __expf(-dot<KPL>(u, p)));
+            float loss = tp.weight * (pred - (tp.y > 0 ? 1.0f : 0.0f));
+            float gi[KPL], gu[KPL];
+#pragma unroll
+            for (int k = 0; k < KPL; k++) { gi[k] = loss * u.v[k]; gu[k] = loss * p.v[k]; }
+            int n1, n2;
+            lrsum += scatter<KPL, ADADELTA>(a.itf, m.item, m, tp.item, gi, loss, alpha_i, lane, n1);
+            lrsum += scatter<KPL, ADADELTA>(a.usf, m.user, m, user, gu, loss, alpha_u, lane, n2);
+            nnz_total = n1 + n2;
+            updated = true;
+            c_pos++; c_upd++;
+        } else {
+            int pos_id = tp.item;
+            float pp = 0.0f;
+            const int ps = __ldg(a.pos.indptr + user), pe = __ldg(a.pos.indptr + user + 1);
+            uint32_t ctr = 0;  // philox block counter for this tuple
+            Philox4 rnd = lfm_philox((uint32_t)t, (uint32_t)(t >> 32), ctr++, 0u, a.seed, 0x4c464d31u);
+            int rpos = 0;
+            auto next_u32 = [&]() -> uint32_t {
+                if (rpos == 4) {
+                    rnd = lfm_philox((uint32_t)t, (uint32_t)(t >> 32), ctr++, 0u, a.seed, 0x4c464d31u);
+                    rpos = 0;
+                }
+                uint32_t r = rpos == 0 ? rnd.x : rpos == 1 ? rnd.y : rpos == 2 ? rnd.z : rnd.w;
+                rpos++;
+                return r;
+            };
+
+            if (LOSS == LOSS_KOS) {
+                if (pe == ps) continue;
+                int no_pos = min(a.nkos, pe - ps);  // host guarantees nkos <= 32 in this mode
+                int my_idx = 0;
+                float my_val = 0.0f;
+                for (int j = 0; j < no_pos; j++) {
+                    int sid = __ldg(a.pos.indices + ps + lfm_bounded(next_u32(), (uint32_t)(pe - ps)));
+                    gather<KPL>(a.itf, m.item, d, sid, item_scale, p, lane);
+                    float s = dot<KPL>(u, p);
+                    if (lane == j) { my_idx = sid; my_val = s; }
+                }
+                // position in the stable descending order == what qsort(reverse_pair_compare) yields
+                int rank = 0;
+                for (int j = 0; j < no_pos; j++) {
+                    float vj = __shfl_sync(LFM_FULL, my_val, j);
+                    rank += (vj > my_val || (vj == my_val && j < lane)) ? 1 : 0;
+                }
+                int sel = min(a.k, no_pos) - 1;
+                unsigned hit = __ballot_sync(LFM_FULL, lane < no_pos && rank == sel);
+                int src = __ffs(hit) - 1;
+                if (src < 0) src = 0;  // NaN scores: fall back to the first sample
+                pos_id = __shfl_sync(LFM_FULL, my_idx, src);
+                pp = __shfl_sync(LFM_FULL, my_val, src);
+                gather<KPL>(a.itf, m.item, d, pos_id, item_scale, p, lane);
+                c_pos++;
+            } else {
+                gather<KPL>(a.itf, m.item, d, pos_id, item_scale, p, lane);
+                pp = dot<KPL>(u, p);
+                c_pos++;
+            }
+
+            int neg_id = -1;
+            float loss = 0.0f;
+            if (LOSS == LOSS_BPR) {
+                int tries = 0;
+                do {  // T:1123-1127: popularity-weighted draw from the interaction list
+                    int64_t j = (int64_t)(((unsigned long long)next_u32() * (unsigned long long)a.n) >> 32);
+                    neg_id = __ldg(a.item_ids + j);
+                    c_neg++;
+                    tries++;
+                    if (!lfm_warp_member(a.pos.indices, ps, pe, neg_id, lane)) break;
+                    c_rej++;
+                } while (tries < 256);
+                gather<KPL>(a.itf, m.item, d, neg_id, item_scale, q, lane);
+                float np = dot<KPL>(u, q);
+                loss = tp.weight * (1.0f - 1.0f / (1.0f + __expf(-(pp - np))));
+                updated = true;
+            } else {
+                int sampled = 0;
+                while (sampled < m.max_sampled) {
+                    sampled++;
+                    int cand = lfm_bounded(next_u32(), (uint32_t)n_items);
+                    gather<KPL>(a.itf, m.item, d, cand, item_scale, q, lane);
+                    float np = dot<KPL>(u, q);
+                    c_neg++;
+                    if (np > pp - 1.0f) {
+                        if (lfm_warp_member(a.pos.indices, ps, pe, cand, lane)) { c_rej++; continue; }
+                        float l = (float)a.loss_table[sampled];
+                        loss = (LOSS == LOSS_KOS) ? l : tp.weight * l;
+                        if (loss > (float)LFM_MAX_LOSS) loss = (float)LFM_MAX_LOSS;
+                        neg_id = cand;
+                        updated = true;
+                        break;
+                    }
+                }
+            }
+            if (updated) {
+                float gp[KPL], gn[KPL], gu[KPL];
+#pragma unroll
+                for (int k = 0; k < KPL; k++) {
+                    gp[k] = -loss * u.v[k];
+                    gn[k] = loss * u.v[k];
+                    gu[k] = loss * (q.v[k] - p.v[k]);
+                }
+                int n1, n2, n3;
+                lrsum += scatter<KPL, ADADELTA>(a.itf, m.item, m, pos_id, gp, -loss, alpha_i, lane, n1);
+                lrsum += scatter<KPL, ADADELTA>(a.itf, m.item, m, neg_id, gn, loss, alpha_i, lane, n2);
+                lrsum += scatter<KPL, ADADELTA>(a.usf, m.user, m, user, gu, loss, alpha_u, lane, n3);
+                nnz_total = n1 + n2 + n3;
+                c_upd++;
+            }
+        }
+
+        if (REG && updated) {
+            // T:528-534 / T:640-649 in the log domain; flushed to the global scale every 16 tuples.
+            float avg = lfm_warp_sum(lrsum) / (float)((d + 1) * nnz_total);
+            rs.loc_i += log1p(a.item_alpha * (double)avg);
+            rs.loc_u += log1p(a.user_alpha * (double)avg);
+            if (++rs.pending == 16) {
+                if (lane == 0) {
+                    atomicAdd(&a.scales->item_scale, rs.loc_i);
+                    atomicAdd(&a.scales->user_scale, rs.loc_u);
+                }
+                rs.base_i = __ldcg(&a.scales->item_scale);
+                rs.base_u = __ldcg(&a.scales->user_scale);
+                rs.loc_i = rs.loc_u = 0.0;
+                rs.pending = 0;
+            }
+        }
+    }
+    if (REG && rs.pending && lane == 0) {
+        atomicAdd(&a.scales->item_scale, rs.loc_i);
+        atomicAdd(&a.scales->user_scale, rs.loc_u);
+    }
+    if (lane == 0) {
+        atomicAdd(&a.counters->positives, c_pos);
+        atomicAdd(&a.counters->negatives, c_neg);
+        atomicAdd(&a.counters->updates, c_upd);
+        atomicAdd(&a.counters->rejected, c_rej);
+    }
+}
+
+// Hogwild-mode regularize: scales live in the log domain.
+__global__ void regularize_log_kernel(DevModel m, DevScales* scales) {
+    float is = (float)exp(scales->item_scale), us = (float)exp(scales->user_scale);
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t ni = (size_t)m.item.n * m.d, nu = (size_t)m.user.n * m.d;
+    for (size_t i = tid; i < ni; i += stride) m.item.w[i] = m.item.w[i] / is;
+    for (size_t i = tid; i < (size_t)m.item.n; i += stride) m.item.b[i] = m.item.b[i] / is;
+    for (size_t i = tid; i < nu; i += stride) m.user.w[i] = m.user.w[i] / us;
+    for (size_t i = tid; i < (size_t)m.user.n; i += stride) m.user.b[i] = m.user.b[i] / us;
+}
+__global__ void reset_scales_kernel(DevScales* s) { s->item_scale = 0.0; s->user_scale = 0.0; }
+
+template <int LOSS, int KPL>
+cudaError_t launch_generic(const FitArgs& a, const Tuple* tuples, int64_t begin, int64_t count,
+                           cudaStream_t st) {
+    FitArgs b = a;
+    b.n = count;
+    const Tuple* tp = tuples + begin;
+    bool reg = (a.item_alpha != 0.0 || a.user_alpha != 0.0);
+    int block = 256;
+    int64_t warps_needed = count;
+    int64_t blocks = (warps_needed * 32 + block - 1) / block;
+    int64_t cap = 148 * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    if (a.model.adadelta) {
+        if (reg) hogwild_kernel<LOSS, KPL, true, true><<<(int)blocks, block, 0, st>>>(b, tp);
+        else hogwild_kernel<LOSS, KPL, true, false><<<(int)blocks, block, 0, st>>>(b, tp);
+    } else {
+        if (reg) hogwild_kernel<LOSS, KPL, false, true><<<(int)blocks, block, 0, st>>>(b, tp);
+        else hogwild_kernel<LOSS, KPL, false, false><<<(int)blocks, block, 0, st>>>(b, tp);
+    }
+    return cudaGetLastError();
+}
+
+template <int LOSS>
+cudaError_t launch_generic_kpl(const FitArgs& a, const Tuple* tuples, int64_t begin, int64_t count,
+                               cudaStream_t st) {
+    int d = a.model.d;
+    if (d <= 32) return launch_generic<LOSS, 1>(a, tuples, begin, count, st);
+    if (d <= 64) return launch_generic<LOSS, 2>(a, tuples, begin, count, st);
+    if (d <= 128) return launch_generic<LOSS, 4>(a, tuples, begin, count, st);
+    if (d <= 256) return launch_generic<LOSS, 8>(a, tuples, begin, count, st);
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace
+
+#include "lfm_hogwild_fast.cuh"
+
+// Host-visible helper: is (loss, model, features) eligible for the hogwild path at all?
+extern "C" int lfm_hogwild_supported(int loss, int d, int nkos) {
+    if (d < 1 || d > 256) return 0;
+    if (loss == LOSS_KOS && nkos > 32) return 0;
+    return 1;
+}
+
+cudaError_t lfm_launch_pack(const FitArgs& a, int loss, Tuple* tuples, uint32_t perm_key,
+                            cudaStream_t st) {
+    if (a.n == 0) return cudaSuccess;
+    int bits = 1;
+    while (((int64_t)1 << bits) < a.n) bits++;
+    int hb = (bits + 1) / 2;
+    if (hb < 1) hb = 1;
+    int64_t blocks = (a.n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    int skip = (loss == LOSS_WARP || loss == LOSS_BPR) ? 1 : 0;
+    pack_kernel<<<(int)blocks, 256, 0, st>>>(a.user_ids, loss == LOSS_KOS ? nullptr : a.item_ids,
+                                             loss == LOSS_KOS ? nullptr : a.y,
+                                             loss == LOSS_KOS ? nullptr : a.sample_weight, a.shuffle,
+                                             a.n, hb, perm_key, skip, tuples);
+    return cudaGetLastError();
+}
+
+// Runs one epoch in hogwild mode.  With L2 regularisation the epoch is cut into
+// segments so the host-visible rescale check (T:901-904) happens between launches.
+cudaError_t lfm_launch_hogwild(int loss, const FitArgs& a, Tuple* tuples, cudaStream_t st,
+                               int* launches, cudaEvent_t ev_train_begin, cudaEvent_t ev_train_end) {
+    cudaError_t e = lfm_launch_pack(a, loss, tuples, a.seed ^ 0x5bd1e995u, st);
+    if (e != cudaSuccess) return e;
+    if (launches) (*launches)++;
+    bool reg = (a.item_alpha != 0.0 || a.user_alpha != 0.0);
+    if (reg) { reset_scales_kernel<<<1, 1, 0, st>>>(a.scales); if (launches) (*launches)++; }
+    if (ev_train_begin) cudaEventRecord(ev_train_begin, st);
+    if (a.n == 0) {
+        if (ev_train_end) cudaEventRecord(ev_train_end, st);
+        return cudaSuccess;
+    }
+    int64_t seg = reg ? (int64_t)1 << 21 : a.n;
+    for (int64_t begin = 0; begin < a.n; begin += seg) {
+        int64_t count = (a.n - begin < seg) ? (a.n - begin) : seg;
+        bool done = false;
+        e = lfm_try_launch_fast(loss, a, tuples, begin, count, st, &done);
+        if (e != cudaSuccess) return e;
+        if (!done) {
+            switch (loss) {
+                case LOSS_LOGISTIC: e = launch_generic_kpl<LOSS_LOGISTIC>(a, tuples, begin, count, st); break;
+                case LOSS_WARP: e = launch_generic_kpl<LOSS_WARP>(a, tuples, begin, count, st); break;
+                case LOSS_BPR: e = launch_generic_kpl<LOSS_BPR>(a, tuples, begin, count, st); break;
+                case LOSS_KOS: e = launch_generic_kpl<LOSS_KOS>(a, tuples, begin, count, st); break;
+                default: return cudaErrorInvalidValue;
+            }
+            if (e != cudaSuccess) return e;
+        }
+        if (launches) (*launches)++;
+        if (reg && begin + seg < a.n) {
+            // mid-epoch rescale (T:901-904): check the scales between segments
+            DevScales h;
+            e = cudaMemcpyAsync(&h, a.scales, sizeof(h), cudaMemcpyDeviceToHost, st);
+            if (e != cudaSuccess) return e;
+            e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) return e;
+            if (h.item_scale > 13.815510557964274 || h.user_scale > 13.815510557964274) {  // ln(1e6)
+                regularize_log_kernel<<<148 * 8, 256, 0, st>>>(a.model, a.scales);
+                reset_scales_kernel<<<1, 1, 0, st>>>(a.scales);
+                if (launches) (*launches) += 2;
+            }
+        }
+    }
+    if (ev_train_end) cudaEventRecord(ev_train_end, st);
+    if (reg) {
+        regularize_log_kernel<<<148 * 8, 256, 0, st>>>(a.model, a.scales);
+        if (launches) (*launches)++;
+    }
+    return cudaGetLastError();
+}

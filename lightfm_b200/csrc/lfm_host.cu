@@ -1,0 +1,789 @@
+// lfm_host.cu -- the C ABI of libfm_cuda.so (include/lfm_cuda.h): host-pointer entry
+// points that stage inputs into HBM, launch the kernels and write results back in place,
+// mirroring the in-place contract of the reference's Cython functions.
+//
+// No CPU fallback lives here: without a CUDA device every compute entry returns
+// LFM_ERR_CUDA with a message.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "lfm_common.cuh"
+
+extern "C" size_t lfm_ranks_scratch_floats(int n_items, int d, int test_rows);
+extern "C" int lfm_hogwild_supported(int loss, int d, int nkos);
+
+namespace {
+
+thread_local char g_err[512] = "";
+int g_mode = LFM_MODE_AUTO;
+int g_device = 0;
+std::mutex g_mu;  // the staging arena is process-global; host entry points serialise on it
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                       \
+    do {                                                                               \
+        cudaError_t e__ = (call);                                                      \
+        if (e__ != cudaSuccess)                                                        \
+            return fail(e__ == cudaErrorMemoryAllocation ? LFM_ERR_OOM : LFM_ERR_CUDA, \
+                        "%s failed: %s", #call, cudaGetErrorString(e__));              \
+    } while (0)
+
+// ---- device staging arena: named buffers that only grow -------------------------
+struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+typedef std::unordered_map<std::string, Buf> Arena;
+Arena g_arena;
+Arena* g_cur = &g_arena;  // arena the staging helpers allocate from (global, or a plan's own)
+cudaStream_t g_stream = nullptr;
+cudaEvent_t g_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+bool g_init = false;
+
+int ensure_init() {
+    if (g_init) return LFM_OK;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(LFM_ERR_CUDA, "no usable CUDA device (%s); libfm_cuda has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    CU(cudaSetDevice(g_device));
+    CU(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 6; i++) CU(cudaEventCreate(&g_ev[i]));
+    g_init = true;
+    return LFM_OK;
+}
+
+int arena_get(const char* name, size_t bytes, void** out) {
+    Buf& b = (*g_cur)[name];
+    if (bytes == 0) bytes = 16;
+    if (b.cap < bytes) {
+        if (b.p) cudaFree(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&b.p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            e = cudaMalloc(&b.p, bytes);
+            want = bytes;
+        }
+        if (e != cudaSuccess) {
+            b.p = nullptr;
+            return fail(LFM_ERR_OOM, "cudaMalloc(%zu bytes) for '%s' failed: %s", bytes, name,
+                        cudaGetErrorString(e));
+        }
+        b.cap = want;
+    }
+    *out = b.p;
+    return LFM_OK;
+}
+
+struct Xfer {  // byte accounting for one call
+    int64_t h2d = 0, d2h = 0;
+};
+
+template <typename T>
+int upload(const char* name, const T* host, size_t count, T** dev, Xfer& x) {
+    void* p = nullptr;
+    int rc = arena_get(name, count * sizeof(T), &p);
+    if (rc != LFM_OK) return rc;
+    if (count) {
+        if (!host) return fail(LFM_ERR_ARG, "null host pointer for '%s'", name);
+        CU(cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, g_stream));
+        x.h2d += (int64_t)(count * sizeof(T));
+    }
+    *dev = (T*)p;
+    return LFM_OK;
+}
+
+template <typename T>
+int download(T* host, const T* dev, size_t count, Xfer& x) {
+    if (count) {
+        CU(cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, g_stream));
+        x.d2h += (int64_t)(count * sizeof(T));
+    }
+    return LFM_OK;
+}
+
+int check_csr(const lfm_csr* c, const char* what, bool need_data) {
+    if (!c) return fail(LFM_ERR_ARG, "%s: null CSR", what);
+    if (c->rows < 0 || c->cols < 0 || c->nnz < 0) return fail(LFM_ERR_ARG, "%s: negative size", what);
+    if (!c->indptr) return fail(LFM_ERR_ARG, "%s: null indptr", what);
+    if (c->nnz > 0 && (!c->indices || (need_data && !c->data)))
+        return fail(LFM_ERR_ARG, "%s: null indices/data with nnz > 0", what);
+    return LFM_OK;
+}
+
+int upload_csr(const char* name, const lfm_csr* c, bool need_data, bool detect_identity, DevCsr* out,
+               Xfer& x) {
+    int rc = check_csr(c, name, need_data);
+    if (rc != LFM_OK) return rc;
+    std::string base(name);
+    int32_t *indptr = nullptr, *indices = nullptr;
+    float* data = nullptr;
+    rc = upload((base + ".indptr").c_str(), c->indptr, (size_t)c->rows + 1, &indptr, x);
+    if (rc != LFM_OK) return rc;
+    rc = upload((base + ".indices").c_str(), c->indices, (size_t)c->nnz, &indices, x);
+    if (rc != LFM_OK) return rc;
+    if (need_data) {
+        rc = upload((base + ".data").c_str(), c->data, (size_t)c->nnz, &data, x);
+        if (rc != LFM_OK) return rc;
+    }
+    out->indptr = indptr;
+    out->indices = indices;
+    out->data = data;
+    out->rows = c->rows;
+    out->cols = c->cols;
+    out->nnz = c->nnz;
+    out->identity = 0;
+    if (detect_identity && need_data && c->rows == c->cols && c->nnz == (int64_t)c->rows && c->rows > 0) {
+        int32_t* flag = nullptr;
+        void* p = nullptr;
+        rc = arena_get((base + ".idflag").c_str(), sizeof(int32_t), &p);
+        if (rc != LFM_OK) return rc;
+        flag = (int32_t*)p;
+        int32_t one = 1, h = 0;
+        CU(cudaMemcpyAsync(flag, &one, sizeof(one), cudaMemcpyHostToDevice, g_stream));
+        CU(lfm_launch_check_identity(*out, flag, g_stream));
+        CU(cudaMemcpyAsync(&h, flag, sizeof(h), cudaMemcpyDeviceToHost, g_stream));
+        CU(cudaStreamSynchronize(g_stream));
+        out->identity = h;
+    }
+    return LFM_OK;
+}
+
+int check_model(const lfm_model* m) {
+    if (!m) return fail(LFM_ERR_ARG, "null model");
+    if (m->no_components < 1) return fail(LFM_ERR_ARG, "no_components must be >= 1");
+    if (m->n_item_features < 0 || m->n_user_features < 0) return fail(LFM_ERR_ARG, "negative table size");
+    const float* req[] = {m->item_features, m->item_feature_gradients, m->item_biases,
+                          m->item_bias_gradients, m->user_features, m->user_feature_gradients,
+                          m->user_biases, m->user_bias_gradients};
+    for (const float* p : req)
+        if (!p && (m->n_item_features > 0 && m->n_user_features > 0))
+            return fail(LFM_ERR_ARG, "null model array");
+    if (m->adadelta && (!m->item_feature_momentum || !m->item_bias_momentum ||
+                        !m->user_feature_momentum || !m->user_bias_momentum))
+        return fail(LFM_ERR_ARG, "adadelta needs the momentum arrays");
+    return LFM_OK;
+}
+
+// Upload the model.  `train`: also stage accumulators (and momentum for adadelta).
+int upload_model(const lfm_model* m, bool train, DevModel* out, Xfer& x) {
+    int rc = check_model(m);
+    if (rc != LFM_OK) return rc;
+    size_t d = (size_t)m->no_components;
+    size_t ni = (size_t)m->n_item_features, nu = (size_t)m->n_user_features;
+    memset(out, 0, sizeof(*out));
+    out->d = m->no_components;
+    out->adadelta = m->adadelta;
+    out->lr = m->learning_rate;
+    out->rho = m->rho;
+    out->eps = m->eps;
+    out->max_sampled = m->max_sampled;
+    out->item.n = m->n_item_features;
+    out->user.n = m->n_user_features;
+#define UP(field, src, cnt)                                    \
+    rc = upload("model." #field, (const float*)src, cnt, &out->field, x); \
+    if (rc != LFM_OK) return rc;
+    UP(item.w, m->item_features, ni * d)
+    UP(item.b, m->item_biases, ni)
+    UP(user.w, m->user_features, nu * d)
+    UP(user.b, m->user_biases, nu)
+    if (train) {
+        UP(item.g, m->item_feature_gradients, ni * d)
+        UP(item.bg, m->item_bias_gradients, ni)
+        UP(user.g, m->user_feature_gradients, nu * d)
+        UP(user.bg, m->user_bias_gradients, nu)
+        if (m->adadelta) {
+            UP(item.m, m->item_feature_momentum, ni * d)
+            UP(item.bm, m->item_bias_momentum, ni)
+            UP(user.m, m->user_feature_momentum, nu * d)
+            UP(user.bm, m->user_bias_momentum, nu)
+        }
+    }
+#undef UP
+    return LFM_OK;
+}
+
+int download_model(lfm_model* m, const DevModel& dm, Xfer& x) {
+    size_t d = (size_t)m->no_components;
+    size_t ni = (size_t)m->n_item_features, nu = (size_t)m->n_user_features;
+    int rc;
+#define DN(dst, field, cnt)                 \
+    rc = download(dst, dm.field, cnt, x);   \
+    if (rc != LFM_OK) return rc;
+    DN(m->item_features, item.w, ni * d)
+    DN(m->item_feature_gradients, item.g, ni * d)
+    DN(m->item_biases, item.b, ni)
+    DN(m->item_bias_gradients, item.bg, ni)
+    DN(m->user_features, user.w, nu * d)
+    DN(m->user_feature_gradients, user.g, nu * d)
+    DN(m->user_biases, user.b, nu)
+    DN(m->user_bias_gradients, user.bg, nu)
+    if (m->adadelta) {
+        DN(m->item_feature_momentum, item.m, ni * d)
+        DN(m->item_bias_momentum, item.bm, ni)
+        DN(m->user_feature_momentum, user.m, nu * d)
+        DN(m->user_bias_momentum, user.bm, nu)
+    }
+#undef DN
+    return LFM_OK;
+}
+
+int resolve_mode(int num_threads, int loss, int d, int nkos) {
+    int mode = g_mode;
+    if (mode == LFM_MODE_AUTO) mode = (num_threads <= 1) ? LFM_MODE_REPLAY : LFM_MODE_HOGWILD;
+    if (mode == LFM_MODE_HOGWILD && !lfm_hogwild_supported(loss, d, nkos)) mode = LFM_MODE_REPLAY;
+    return mode;
+}
+
+struct FitInputs {
+    const lfm_csr *itf, *usf, *pos;
+    const int32_t *user_ids, *item_ids;
+    const float *y, *w;
+    const int32_t* shuffle;
+    int64_t n;
+    lfm_model* model;
+    double item_alpha, user_alpha;
+    int k, nkos;
+    int num_threads;
+    const uint32_t* seeds;
+    int n_seeds;
+};
+
+struct Staged {
+    FitArgs a;
+    int loss = 0;
+    Xfer x;
+    std::vector<double> table;
+};
+
+// Validate + upload everything one epoch needs.  `with_shuffle`: stage the host shuffle too.
+int stage_fit(int loss, const FitInputs& in, bool with_shuffle, Staged* out) {
+    if (in.n < 0) return fail(LFM_ERR_ARG, "negative no_examples");
+    if (in.n > 0 && (!in.user_ids || (with_shuffle && !in.shuffle)))
+        return fail(LFM_ERR_ARG, "null id / shuffle array");
+    if (loss != LOSS_KOS && in.n > 0 && (!in.item_ids || !in.y || !in.w))
+        return fail(LFM_ERR_ARG, "null item_ids / Y / sample_weight");
+    if (in.n > 0x7fffffffLL) return fail(LFM_ERR_ARG, "no_examples exceeds int32 (reference limit)");
+    int rc = check_model(in.model);
+    if (rc != LFM_OK) return rc;
+    rc = ensure_init();
+    if (rc != LFM_OK) return rc;
+
+    Xfer& x = out->x;
+    FitArgs& a = out->a;
+    memset(&a, 0, sizeof(a));
+    out->loss = loss;
+    rc = upload_csr("itf", in.itf, true, true, &a.itf, x);
+    if (rc != LFM_OK) return rc;
+    rc = upload_csr("usf", in.usf, true, true, &a.usf, x);
+    if (rc != LFM_OK) return rc;
+    if (loss != LOSS_LOGISTIC) {
+        rc = upload_csr("pos", in.pos, false, false, &a.pos, x);
+        if (rc != LFM_OK) return rc;
+    }
+    rc = upload_model(in.model, true, &a.model, x);
+    if (rc != LFM_OK) return rc;
+    if (a.itf.cols > a.model.item.n || a.usf.cols > a.model.user.n)
+        return fail(LFM_ERR_ARG, "feature matrix has more columns than the model has embeddings");
+
+    int32_t *d_users = nullptr, *d_items = nullptr, *d_shuffle = nullptr;
+    float *d_y = nullptr, *d_w = nullptr;
+    rc = upload("fit.user_ids", in.user_ids, (size_t)in.n, &d_users, x);
+    if (rc != LFM_OK) return rc;
+    if (with_shuffle) {
+        rc = upload("fit.shuffle", in.shuffle, (size_t)in.n, &d_shuffle, x);
+        if (rc != LFM_OK) return rc;
+    }
+    if (loss != LOSS_KOS) {
+        rc = upload("fit.item_ids", in.item_ids, (size_t)in.n, &d_items, x);
+        if (rc != LFM_OK) return rc;
+        rc = upload("fit.y", in.y, (size_t)in.n, &d_y, x);
+        if (rc != LFM_OK) return rc;
+        if (in.w == in.y) {
+            d_w = d_y;  // lightfm.py:412-415 aliases sample_weight to interactions.data
+        } else {
+            rc = upload("fit.w", in.w, (size_t)in.n, &d_w, x);
+            if (rc != LFM_OK) return rc;
+        }
+    }
+    a.user_ids = d_users;
+    a.item_ids = d_items;
+    a.y = d_y;
+    a.sample_weight = d_w;
+    a.shuffle = d_shuffle;
+    a.n = in.n;
+    a.item_alpha = in.item_alpha;
+    a.user_alpha = in.user_alpha;
+    a.k = in.k;
+    a.nkos = in.nkos;
+
+    // log terms of the WARP loss (T:881 / T:1039) precomputed with the host libm so that
+    // replay mode is bit-identical to the reference: loss_table[s] for s in 1..max_sampled
+    int ms = a.model.max_sampled > 0 ? a.model.max_sampled : 0;
+    out->table.assign((size_t)ms + 1, 0.0);
+    for (int s = 1; s <= ms; s++) {
+        double fl = floor((double)((a.itf.rows - 1) / s));
+        out->table[s] = (loss == LOSS_KOS) ? log(fl) : log(fl > 1.0 ? fl : 1.0);
+    }
+    double* d_table = nullptr;
+    rc = upload("fit.loss_table", out->table.data(), out->table.size(), &d_table, x);
+    if (rc != LFM_OK) return rc;
+    a.loss_table = d_table;
+
+    void* p = nullptr;
+    rc = arena_get("fit.counters", sizeof(DevCounters), &p);
+    if (rc != LFM_OK) return rc;
+    a.counters = (DevCounters*)p;
+    rc = arena_get("fit.scales", sizeof(DevScales), &p);
+    if (rc != LFM_OK) return rc;
+    a.scales = (DevScales*)p;
+    return LFM_OK;
+}
+
+// Launch one epoch on staged (device-resident) data.
+int run_fit(Staged& st, int mode, uint32_t seed, int* launches) {
+    FitArgs& a = st.a;
+    a.seed = seed;
+    CU(cudaMemsetAsync(a.counters, 0, sizeof(DevCounters), g_stream));
+    DevScales ones = {1.0, 1.0};
+    CU(cudaMemcpyAsync(a.scales, &ones, sizeof(ones), cudaMemcpyHostToDevice, g_stream));
+    if (mode == LFM_MODE_REPLAY) {
+        if (a.n == 0) {
+            CU(cudaEventRecord(g_ev[4], g_stream));
+            CU(cudaEventRecord(g_ev[5], g_stream));
+        }
+        if (a.n > 0) {
+            if (!a.shuffle) return fail(LFM_ERR_STATE, "replay mode needs the host shuffle order");
+            CU(cudaEventRecord(g_ev[4], g_stream));
+            CU(lfm_launch_replay(st.loss, a, g_stream));
+            CU(cudaEventRecord(g_ev[5], g_stream));
+            (*launches)++;
+            DevScales h;
+            CU(cudaMemcpyAsync(&h, a.scales, sizeof(h), cudaMemcpyDeviceToHost, g_stream));
+            CU(cudaStreamSynchronize(g_stream));
+            // final regularize (T:910-912): x / 1.0 == x, so skip the sweep when both are exactly 1
+            if (!(h.item_scale == 1.0 && h.user_scale == 1.0)) {
+                CU(lfm_launch_regularize(a.model, a.scales, g_stream));
+                (*launches)++;
+            }
+        }
+    } else {
+        void* p = nullptr;
+        int rc = arena_get("fit.tuples", sizeof(Tuple) * (size_t)(a.n > 0 ? a.n : 1), &p);
+        if (rc != LFM_OK) return rc;
+        CU(lfm_launch_hogwild(st.loss, a, (Tuple*)p, g_stream, launches, g_ev[4], g_ev[5]));
+    }
+    return LFM_OK;
+}
+
+uint32_t fold_seed(int loss, int mode, const uint32_t* seeds, int n_seeds) {
+    // rand_r stream (replay: thread 0's seed) / philox key (hogwild: all seeds folded together)
+    if (loss == LOSS_LOGISTIC || !seeds || n_seeds < 1) return 0x1f2e3d4cu;
+    uint32_t seed = seeds[0];
+    if (mode == LFM_MODE_HOGWILD)
+        for (int i = 1; i < n_seeds; i++) seed = seed * 0x9E3779B1u + seeds[i];
+    return seed;
+}
+
+void fill_counters(lfm_counters* c, const DevCounters& hc, const Xfer& x, int launches, int mode,
+                   float ms_h2d, float ms_k, float ms_d2h) {
+    if (!c) return;
+    c->positives = (int64_t)hc.positives;
+    c->negatives_drawn = (int64_t)hc.negatives;
+    c->updates = (int64_t)hc.updates;
+    c->rejected = (int64_t)hc.rejected;
+    c->kernel_ms = ms_k;
+    float ms_train = 0;
+    cudaEventElapsedTime(&ms_train, g_ev[4], g_ev[5]);
+    c->train_kernel_ms = ms_train;
+    c->h2d_ms = ms_h2d;
+    c->d2h_ms = ms_d2h;
+    c->h2d_bytes = x.h2d;
+    c->d2h_bytes = x.d2h;
+    c->kernel_launches = launches;
+    c->mode = mode;
+}
+
+int fit_common(int loss, const FitInputs& in, lfm_counters* counters) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (counters) memset(counters, 0, sizeof(*counters));
+    if (loss != LOSS_LOGISTIC && (!in.seeds || in.n_seeds < 1))
+        return fail(LFM_ERR_ARG, "random_states must hold at least one seed");
+    int rc = ensure_init();
+    if (rc != LFM_OK) return rc;
+    g_cur = &g_arena;
+    Staged st;
+    CU(cudaEventRecord(g_ev[0], g_stream));
+    rc = stage_fit(loss, in, true, &st);
+    if (rc != LFM_OK) return rc;
+    const int mode = resolve_mode(in.num_threads, loss, st.a.model.d, in.nkos);
+    CU(cudaEventRecord(g_ev[1], g_stream));
+    int launches = 0;
+    rc = run_fit(st, mode, fold_seed(loss, mode, in.seeds, in.n_seeds), &launches);
+    if (rc != LFM_OK) return rc;
+    CU(cudaEventRecord(g_ev[2], g_stream));
+    rc = download_model(in.model, st.a.model, st.x);
+    if (rc != LFM_OK) return rc;
+    DevCounters hc;
+    CU(cudaMemcpyAsync(&hc, st.a.counters, sizeof(hc), cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaEventRecord(g_ev[3], g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    float ms_h2d = 0, ms_k = 0, ms_d2h = 0;
+    cudaEventElapsedTime(&ms_h2d, g_ev[0], g_ev[1]);
+    cudaEventElapsedTime(&ms_k, g_ev[1], g_ev[2]);
+    cudaEventElapsedTime(&ms_d2h, g_ev[2], g_ev[3]);
+    fill_counters(counters, hc, st.x, launches, mode, ms_h2d, ms_k, ms_d2h);
+    return LFM_OK;
+}
+
+}  // namespace
+
+// ---- library state ----------------------------------------------------------------
+extern "C" const char* lfm_last_error(void) { return g_err; }
+extern "C" const char* lfm_version(void) { return "lightfm_b200 libfm_cuda 0.1 (sm_100a)"; }
+extern "C" int lfm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+extern "C" int lfm_set_device(int device) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (device < 0 || device >= lfm_device_count()) return fail(LFM_ERR_ARG, "no such device %d", device);
+    if (g_init && device != g_device) return fail(LFM_ERR_STATE, "device already initialised as %d", g_device);
+    g_device = device;
+    return LFM_OK;
+}
+extern "C" int lfm_set_mode(int mode) {
+    if (mode < LFM_MODE_AUTO || mode > LFM_MODE_HOGWILD) return fail(LFM_ERR_ARG, "bad mode %d", mode);
+    g_mode = mode;
+    return LFM_OK;
+}
+extern "C" int lfm_get_mode(void) { return g_mode; }
+extern "C" int lfm_release_cache(void) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    for (auto& kv : g_arena)
+        if (kv.second.p) cudaFree(kv.second.p);
+    g_arena.clear();
+    return LFM_OK;
+}
+
+// ---- training entry points ----------------------------------------------------------
+extern "C" int lfm_fit_logistic(const lfm_csr* item_features, const lfm_csr* user_features,
+                                const int32_t* user_ids, const int32_t* item_ids, const float* Y,
+                                const float* sample_weight, const int32_t* shuffle_indices,
+                                int64_t no_examples, lfm_model* model, double item_alpha,
+                                double user_alpha, int32_t num_threads, lfm_counters* counters) {
+    FitInputs in = {item_features, user_features, nullptr, user_ids, item_ids, Y, sample_weight,
+                    shuffle_indices, no_examples, model, item_alpha, user_alpha, 0, 0, num_threads,
+                    nullptr, 0};
+    return fit_common(LOSS_LOGISTIC, in, counters);
+}
+
+extern "C" int lfm_fit_warp(const lfm_csr* item_features, const lfm_csr* user_features,
+                            const lfm_csr* interactions, const int32_t* user_ids,
+                            const int32_t* item_ids, const float* Y, const float* sample_weight,
+                            const int32_t* shuffle_indices, int64_t no_examples, lfm_model* model,
+                            double item_alpha, double user_alpha, int32_t num_threads,
+                            const uint32_t* random_states, int32_t n_random_states,
+                            lfm_counters* counters) {
+    FitInputs in = {item_features, user_features, interactions, user_ids, item_ids, Y, sample_weight,
+                    shuffle_indices, no_examples, model, item_alpha, user_alpha, 0, 0, num_threads,
+                    random_states, n_random_states};
+    return fit_common(LOSS_WARP, in, counters);
+}
+
+extern "C" int lfm_fit_bpr(const lfm_csr* item_features, const lfm_csr* user_features,
+                           const lfm_csr* interactions, const int32_t* user_ids,
+                           const int32_t* item_ids, const float* Y, const float* sample_weight,
+                           const int32_t* shuffle_indices, int64_t no_examples, lfm_model* model,
+                           double item_alpha, double user_alpha, int32_t num_threads,
+                           const uint32_t* random_states, int32_t n_random_states,
+                           lfm_counters* counters) {
+    FitInputs in = {item_features, user_features, interactions, user_ids, item_ids, Y, sample_weight,
+                    shuffle_indices, no_examples, model, item_alpha, user_alpha, 0, 0, num_threads,
+                    random_states, n_random_states};
+    return fit_common(LOSS_BPR, in, counters);
+}
+
+extern "C" int lfm_fit_warp_kos(const lfm_csr* item_features, const lfm_csr* user_features,
+                                const lfm_csr* data, const int32_t* user_ids,
+                                const int32_t* shuffle_indices, int64_t no_examples, lfm_model* model,
+                                double item_alpha, double user_alpha, int32_t k, int32_t n,
+                                int32_t num_threads, const uint32_t* random_states,
+                                int32_t n_random_states, lfm_counters* counters) {
+    if (k < 1 || n < 1) return fail(LFM_ERR_ARG, "k and n must be positive");
+    FitInputs in = {item_features, user_features, data, user_ids, nullptr, nullptr, nullptr,
+                    shuffle_indices, no_examples, model, item_alpha, user_alpha, k, n, num_threads,
+                    random_states, n_random_states};
+    return fit_common(LOSS_KOS, in, counters);
+}
+
+// ---- scoring entry points -------------------------------------------------------------
+extern "C" int lfm_predict_lightfm(const lfm_csr* item_features, const lfm_csr* user_features,
+                                   const int32_t* user_ids, const int32_t* item_ids,
+                                   float* predictions, int64_t no_examples, const lfm_model* model,
+                                   int32_t num_threads) {
+    (void)num_threads;
+    std::lock_guard<std::mutex> lock(g_mu);
+    g_cur = &g_arena;
+    if (no_examples < 0) return fail(LFM_ERR_ARG, "negative no_examples");
+    if (no_examples > 0 && (!user_ids || !item_ids || !predictions)) return fail(LFM_ERR_ARG, "null array");
+    int rc = ensure_init();
+    if (rc != LFM_OK) return rc;
+    Xfer x;
+    DevCsr itf, usf;
+    DevModel dm;
+    rc = upload_csr("itf", item_features, true, false, &itf, x);
+    if (rc != LFM_OK) return rc;
+    rc = upload_csr("usf", user_features, true, false, &usf, x);
+    if (rc != LFM_OK) return rc;
+    rc = upload_model(model, false, &dm, x);
+    if (rc != LFM_OK) return rc;
+    int32_t *du = nullptr, *di = nullptr;
+    rc = upload("predict.user_ids", user_ids, (size_t)no_examples, &du, x);
+    if (rc != LFM_OK) return rc;
+    rc = upload("predict.item_ids", item_ids, (size_t)no_examples, &di, x);
+    if (rc != LFM_OK) return rc;
+    void* p = nullptr;
+    rc = arena_get("predict.out", sizeof(float) * (size_t)no_examples, &p);
+    if (rc != LFM_OK) return rc;
+    CU(lfm_launch_predict(itf, usf, dm, du, di, (float*)p, no_examples, g_stream));
+    rc = download(predictions, (const float*)p, (size_t)no_examples, x);
+    if (rc != LFM_OK) return rc;
+    CU(cudaStreamSynchronize(g_stream));
+    return LFM_OK;
+}
+
+extern "C" int lfm_predict_ranks(const lfm_csr* item_features, const lfm_csr* user_features,
+                                 const lfm_csr* test_interactions, const lfm_csr* train_interactions,
+                                 float* ranks, const lfm_model* model, int32_t num_threads) {
+    (void)num_threads;
+    std::lock_guard<std::mutex> lock(g_mu);
+    g_cur = &g_arena;
+    int rc = check_csr(test_interactions, "test_interactions", false);
+    if (rc != LFM_OK) return rc;
+    rc = check_csr(train_interactions, "train_interactions", false);
+    if (rc != LFM_OK) return rc;
+    if (test_interactions->nnz > 0 && !ranks) return fail(LFM_ERR_ARG, "null ranks");
+    if (train_interactions->rows < test_interactions->rows)
+        return fail(LFM_ERR_ARG, "train_interactions has fewer rows than test_interactions");
+    rc = ensure_init();
+    if (rc != LFM_OK) return rc;
+    Xfer x;
+    DevCsr itf, usf, test, train;
+    DevModel dm;
+    rc = upload_csr("itf", item_features, true, false, &itf, x);
+    if (rc != LFM_OK) return rc;
+    rc = upload_csr("usf", user_features, true, false, &usf, x);
+    if (rc != LFM_OK) return rc;
+    rc = upload_csr("ranks.test", test_interactions, false, false, &test, x);
+    if (rc != LFM_OK) return rc;
+    rc = upload_csr("ranks.train", train_interactions, false, false, &train, x);
+    if (rc != LFM_OK) return rc;
+    rc = upload_model(model, false, &dm, x);
+    if (rc != LFM_OK) return rc;
+    if (itf.rows < test.cols) return fail(LFM_ERR_ARG, "item_features has fewer rows than there are items");
+    if (usf.rows < test.rows) return fail(LFM_ERR_ARG, "user_features has fewer rows than there are users");
+    float* d_ranks = nullptr;
+    rc = upload("ranks.out", ranks, (size_t)test.nnz, &d_ranks, x);
+    if (rc != LFM_OK) return rc;
+    void* p = nullptr;
+    rc = arena_get("ranks.scratch", sizeof(float) * lfm_ranks_scratch_floats(test.cols, dm.d, test.rows), &p);
+    if (rc != LFM_OK) return rc;
+    int launches = 0;
+    CU(lfm_launch_predict_ranks(itf, usf, test, train, dm, d_ranks, (float*)p, g_stream, &launches));
+    rc = download(ranks, (const float*)d_ranks, (size_t)test.nnz, x);
+    if (rc != LFM_OK) return rc;
+    CU(cudaStreamSynchronize(g_stream));
+    return LFM_OK;
+}
+
+extern "C" int lfm_calculate_auc_from_rank(const lfm_csr* ranks, const int32_t* num_train_positives,
+                                           float* rank_data, float* auc, int32_t num_threads) {
+    (void)num_threads;
+    std::lock_guard<std::mutex> lock(g_mu);
+    g_cur = &g_arena;
+    int rc = check_csr(ranks, "ranks", false);
+    if (rc != LFM_OK) return rc;
+    if (ranks->rows > 0 && (!num_train_positives || !auc)) return fail(LFM_ERR_ARG, "null array");
+    if (ranks->nnz > 0 && !rank_data) return fail(LFM_ERR_ARG, "null rank_data");
+    rc = ensure_init();
+    if (rc != LFM_OK) return rc;
+    Xfer x;
+    DevCsr dr;
+    rc = upload_csr("auc.ranks", ranks, false, false, &dr, x);
+    if (rc != LFM_OK) return rc;
+    int32_t* d_ntp = nullptr;
+    float *d_rank = nullptr, *d_auc = nullptr;
+    rc = upload("auc.ntp", num_train_positives, (size_t)ranks->rows, &d_ntp, x);
+    if (rc != LFM_OK) return rc;
+    rc = upload("auc.rank_data", (const float*)rank_data, (size_t)ranks->nnz, &d_rank, x);
+    if (rc != LFM_OK) return rc;
+    rc = upload("auc.auc", (const float*)auc, (size_t)ranks->rows, &d_auc, x);
+    if (rc != LFM_OK) return rc;
+    CU(lfm_launch_auc(dr, d_ntp, d_rank, d_auc, g_stream));
+    rc = download(rank_data, (const float*)d_rank, (size_t)ranks->nnz, x);
+    if (rc != LFM_OK) return rc;
+    rc = download(auc, (const float*)d_auc, (size_t)ranks->rows, x);
+    if (rc != LFM_OK) return rc;
+    CU(cudaStreamSynchronize(g_stream));
+    return LFM_OK;
+}
+
+extern "C" int lfm_test_in_positives(int32_t row, int32_t col, const lfm_csr* mat) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    g_cur = &g_arena;
+    int rc = check_csr(mat, "mat", false);
+    if (rc != LFM_OK) return rc;
+    if (row < 0 || row >= mat->rows) return fail(LFM_ERR_ARG, "row out of range");
+    rc = ensure_init();
+    if (rc != LFM_OK) return rc;
+    Xfer x;
+    DevCsr dm;
+    rc = upload_csr("tip.mat", mat, false, false, &dm, x);
+    if (rc != LFM_OK) return rc;
+    void* p = nullptr;
+    rc = arena_get("tip.out", sizeof(int32_t), &p);
+    if (rc != LFM_OK) return rc;
+    CU(lfm_launch_in_positives(dm, row, col, (int32_t*)p, g_stream));
+    int32_t h = 0;
+    CU(cudaMemcpyAsync(&h, p, sizeof(h), cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    if (h != 0 && h != 3) return fail(LFM_ERR_STATE, "membership searches disagree (%d)", h);
+    return h ? 1 : 0;
+}
+
+
+// ---- resident plans: keep one training problem in HBM across epochs ----------------
+// (the reference crosses the native boundary once per epoch and
+//  re-wraps everything; a plan uploads interactions, features and the model once,
+//  runs any number of epochs on the device, and writes the model back on request.)
+struct lfm_plan {
+    Arena arena;
+    Staged st;
+    int loss = 0;
+    int nkos = 0;
+    bool has_shuffle_buf = false;
+};
+
+extern "C" int lfm_plan_create(lfm_plan** out, int32_t loss, const lfm_csr* item_features,
+                               const lfm_csr* user_features, const lfm_csr* interactions,
+                               const int32_t* user_ids, const int32_t* item_ids, const float* Y,
+                               const float* sample_weight, int64_t no_examples,
+                               const lfm_model* model, double item_alpha, double user_alpha,
+                               int32_t k, int32_t n) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (!out) return fail(LFM_ERR_ARG, "null plan pointer");
+    if (loss < LOSS_LOGISTIC || loss > LOSS_KOS) return fail(LFM_ERR_ARG, "bad loss %d", loss);
+    int rc = ensure_init();
+    if (rc != LFM_OK) return rc;
+    lfm_plan* p = new lfm_plan();
+    p->loss = loss;
+    p->nkos = n;
+    g_cur = &p->arena;
+    FitInputs in = {item_features, user_features, interactions, user_ids, item_ids, Y, sample_weight,
+                    nullptr, no_examples, const_cast<lfm_model*>(model), item_alpha, user_alpha, k, n,
+                    2, nullptr, 0};
+    rc = stage_fit(loss, in, false, &p->st);
+    if (rc == LFM_OK) {
+        cudaError_t e = cudaStreamSynchronize(g_stream);
+        if (e != cudaSuccess) rc = fail(LFM_ERR_CUDA, "plan upload failed: %s", cudaGetErrorString(e));
+    }
+    g_cur = &g_arena;
+    if (rc != LFM_OK) {
+        for (auto& kv : p->arena)
+            if (kv.second.p) cudaFree(kv.second.p);
+        delete p;
+        return rc;
+    }
+    *out = p;
+    return LFM_OK;
+}
+
+// One epoch on resident data.  shuffle_indices == NULL: the visiting order is a fresh
+// pseudo-random permutation generated on the device from `seed` (hogwild mode only).
+extern "C" int lfm_plan_epoch(lfm_plan* p, const int32_t* shuffle_indices, uint32_t seed,
+                              int32_t num_threads, lfm_counters* counters) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (!p) return fail(LFM_ERR_ARG, "null plan");
+    if (counters) memset(counters, 0, sizeof(*counters));
+    g_cur = &p->arena;
+    struct Restore { ~Restore() { g_cur = &g_arena; } } restore;
+    Staged& st = p->st;
+    const int mode = resolve_mode(num_threads, p->loss, st.a.model.d, p->nkos);
+    Xfer x;
+    CU(cudaEventRecord(g_ev[0], g_stream));
+    if (shuffle_indices) {
+        int32_t* d = nullptr;
+        int rc = upload("fit.shuffle", shuffle_indices, (size_t)st.a.n, &d, x);
+        if (rc != LFM_OK) return rc;
+        st.a.shuffle = d;
+    } else {
+        if (mode == LFM_MODE_REPLAY) return fail(LFM_ERR_ARG, "replay mode needs shuffle_indices");
+        st.a.shuffle = nullptr;
+    }
+    CU(cudaEventRecord(g_ev[1], g_stream));
+    int launches = 0;
+    int rc = run_fit(st, mode, seed, &launches);
+    if (rc != LFM_OK) return rc;
+    CU(cudaEventRecord(g_ev[2], g_stream));
+    DevCounters hc;
+    CU(cudaMemcpyAsync(&hc, st.a.counters, sizeof(hc), cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaEventRecord(g_ev[3], g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    float ms_h2d = 0, ms_k = 0, ms_d2h = 0;
+    cudaEventElapsedTime(&ms_h2d, g_ev[0], g_ev[1]);
+    cudaEventElapsedTime(&ms_k, g_ev[1], g_ev[2]);
+    cudaEventElapsedTime(&ms_d2h, g_ev[2], g_ev[3]);
+    fill_counters(counters, hc, x, launches, mode, ms_h2d, ms_k, ms_d2h);
+    return LFM_OK;
+}
+
+// Copy the resident model state back into the caller's arrays.
+extern "C" int lfm_plan_download(lfm_plan* p, lfm_model* model) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (!p || !model) return fail(LFM_ERR_ARG, "null plan / model");
+    const DevModel& dm = p->st.a.model;
+    if (model->no_components != dm.d || model->n_item_features != dm.item.n ||
+        model->n_user_features != dm.user.n || (model->adadelta != 0) != (dm.adadelta != 0))
+        return fail(LFM_ERR_ARG, "model shape does not match the plan");
+    Xfer x;
+    int rc = download_model(model, dm, x);
+    if (rc != LFM_OK) return rc;
+    CU(cudaStreamSynchronize(g_stream));
+    return LFM_OK;
+}
+
+// Device-side divergence check (lightfm.py:447-464): 1 if every parameter is finite.
+extern "C" int lfm_plan_destroy(lfm_plan* p) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (!p) return LFM_OK;
+    if (g_init) cudaStreamSynchronize(g_stream);
+    for (auto& kv : p->arena)
+        if (kv.second.p) cudaFree(kv.second.p);
+    delete p;
+    return LFM_OK;
+}

@@ -1,0 +1,372 @@
+// lfm_replay.cu -- deterministic replay mode (num_threads == 1).
+//
+// One warp walks the shuffled interaction list in the reference's exact order
+// with the reference's rand_r stream and per-element arithmetic, so the result
+// equals the reference at num_threads=1 (oracle/lfm_oracle.c
+// is the CPU statement of the same rules).  Lanes own embedding components
+// (lane l owns components l, l+32, ...): within one SGD step the reference
+// visits component i of the positive row, then the negative row, then the user
+// row, and different components never touch the same address, so running the
+// components on different lanes preserves every per-address op order.
+//
+// THIS FILE MUST BE COMPILED WITH --fmad=false: an FMA would remove a rounding
+// the reference performs.
+//
+// Reference: lightfm/_lightfm_fast.pyx.template ("T:")
+//   compute_representation T:287-317, compute_prediction_from_repr T:320-334,
+//   update_biases T:337-391, update_features T:394-451, update T:454-534,
+//   warp_update T:537-649, regularize T:652-675, fit_logistic T:694-781,
+//   fit_warp T:784-912, fit_warp_kos T:915-1071, fit_bpr T:1074-1182.
+#include "lfm_common.cuh"
+
+namespace {
+
+struct ReplayShared {
+    float* u;       // [d+1]
+    float* pos;     // [d+1]
+    float* neg;     // [d+1]
+    double* lrsum;  // [3*d] per-component learning-rate sums (pos/item, neg, user)
+    int* pidx;      // [nkos]
+    float* pval;    // [nkos]
+};
+
+// T:287-317.  repr[j] = f32(repr[j] + f32(fw * E[f,j])), features in CSR order.
+// Lane l owns components l, l+32, ...; lane 0 also owns the bias slot repr[d]
+// (it is the lane that applies bias steps, so no cross-lane global dependency).
+__device__ void gather(const DevCsr& f, const float* emb, const float* bias, int d, int row,
+                       double scale, float* repr, int lane) {
+    __syncwarp();  // previous readers of repr are done
+    int start = f.indptr[row], stop = f.indptr[row + 1];
+    for (int j = lane; j < d; j += 32) repr[j] = 0.0f;
+    if (lane == 0) repr[d] = 0.0f;
+    for (int i = start; i < stop; i++) {
+        int ft = f.indices[i];
+        float fw = (float)((double)f.data[i] * scale);
+        const float* r = emb + (size_t)ft * d;
+        for (int j = lane; j < d; j += 32) repr[j] = repr[j] + fw * r[j];
+        if (lane == 0) repr[d] = repr[d] + fw * bias[ft];
+    }
+    __syncwarp();
+}
+
+// T:320-334: strictly left-to-right fp32 sum; every lane computes the same value.
+__device__ float score(const float* u, const float* v, int d) {
+    float r = u[d] + v[d];
+    for (int i = 0; i < d; i++) r = r + u[i] * v[i];
+    return r;
+}
+
+__device__ float sigmoid_ref(float v) {  // T:262-267
+    return (float)(1.0 / (1.0 + exp((double)(-v))));
+}
+
+// One parameter step; returns the local learning rate (T:359-389 / T:417-449).
+__device__ double step(float* theta, float* G, float* M, double fw, double gradient, int adadelta,
+                       double lr, double alpha, float rho, float eps) {
+    double llr;
+    if (adadelta) {
+        double t = fw * gradient;
+        float rg = rho * *G;
+        *G = (float)((double)rg + (1.0 - (double)rho) * (t * t));
+        float me = *M + eps, ge = *G + eps;
+        llr = sqrt((double)me) / sqrt((double)ge);
+        double upd = (llr * gradient) * fw;
+        float rm = rho * *M;
+        *M = (float)((double)rm + (1.0 - (double)rho) * (upd * upd));
+        *theta = (float)((double)*theta - upd);
+    } else {
+        llr = lr / sqrt((double)*G);
+        *theta = (float)((double)*theta - (llr * fw) * gradient);
+        double gw = gradient * fw;
+        *G = (float)((double)*G + gw * gw);
+    }
+    *theta = (float)((double)*theta * (1.0 + alpha * llr));
+    return llr;
+}
+
+__device__ double bias_steps(const DevCsr& f, int row, DevTable& t, double gradient,
+                             const DevModel& m, double alpha) {
+    double s = 0.0;
+    int start = f.indptr[row], stop = f.indptr[row + 1];
+    for (int i = start; i < stop; i++) {
+        int ft = f.indices[i];
+        s += step(&t.b[ft], &t.bg[ft], t.bm ? &t.bm[ft] : nullptr, (double)f.data[i], gradient,
+                  m.adadelta, (double)m.lr, alpha, m.rho, m.eps);
+    }
+    return s;
+}
+
+__device__ double row_steps(const DevCsr& f, int row, DevTable& t, int comp, double gradient,
+                            const DevModel& m, double alpha) {
+    double s = 0.0;
+    int start = f.indptr[row], stop = f.indptr[row + 1];
+    for (int i = start; i < stop; i++) {
+        size_t o = (size_t)f.indices[i] * m.d + comp;
+        s += step(&t.w[o], &t.g[o], t.m ? &t.m[o] : nullptr, (double)f.data[i], gradient,
+                  m.adadelta, (double)m.lr, alpha, m.rho, m.eps);
+    }
+    return s;
+}
+
+__device__ int nnz_of(const DevCsr& f, int row) { return f.indptr[row + 1] - f.indptr[row]; }
+
+// T:537-649.  Returns avg learning rate contribution via scales update.
+__device__ void warp_update(FitArgs& a, double loss, int user, int pos_id, int neg_id,
+                            ReplayShared& sh, double& item_scale, double& user_scale, int lane) {
+    DevModel& m = a.model;
+    int d = m.d;
+    double b0 = 0.0, b1 = 0.0, b2 = 0.0;
+    if (lane == 0) {
+        b0 = bias_steps(a.itf, pos_id, m.item, -loss, m, a.item_alpha);
+        b1 = bias_steps(a.itf, neg_id, m.item, loss, m, a.item_alpha);
+        b2 = bias_steps(a.usf, user, m.user, loss, m, a.user_alpha);
+    }
+    for (int i = lane; i < d; i += 32) {
+        float uc = sh.u[i], pc = sh.pos[i], nc = sh.neg[i];
+        sh.lrsum[3 * i + 0] = row_steps(a.itf, pos_id, m.item, i, (-loss) * (double)uc, m, a.item_alpha);
+        sh.lrsum[3 * i + 1] = row_steps(a.itf, neg_id, m.item, i, loss * (double)uc, m, a.item_alpha);
+        sh.lrsum[3 * i + 2] = row_steps(a.usf, user, m.user, i, loss * (double)(float)(nc - pc), m,
+                                        a.user_alpha);
+    }
+    __syncwarp();
+    if (a.item_alpha != 0.0 || a.user_alpha != 0.0) {
+        b0 = __shfl_sync(LFM_FULL, b0, 0);
+        b1 = __shfl_sync(LFM_FULL, b1, 0);
+        b2 = __shfl_sync(LFM_FULL, b2, 0);
+        double avg = 0.0;
+        avg += b0; avg += b1; avg += b2;
+        for (int i = 0; i < 3 * d; i++) avg += sh.lrsum[i];  // same order as T:602-638
+        avg /= (double)((d + 1) * nnz_of(a.usf, user) + (d + 1) * nnz_of(a.itf, pos_id) +
+                        (d + 1) * nnz_of(a.itf, neg_id));
+        item_scale *= (1.0 + a.item_alpha * avg);
+        user_scale *= (1.0 + a.user_alpha * avg);
+    }
+    __syncwarp();
+}
+
+// T:454-534.
+__device__ void logistic_update(FitArgs& a, double loss, int user, int item, ReplayShared& sh,
+                                double& item_scale, double& user_scale, int lane) {
+    DevModel& m = a.model;
+    int d = m.d;
+    double b0 = 0.0, b1 = 0.0;
+    if (lane == 0) {
+        b0 = bias_steps(a.itf, item, m.item, loss, m, a.item_alpha);
+        b1 = bias_steps(a.usf, user, m.user, loss, m, a.user_alpha);
+    }
+    for (int i = lane; i < d; i += 32) {
+        float uc = sh.u[i], ic = sh.pos[i];
+        sh.lrsum[2 * i + 0] = row_steps(a.itf, item, m.item, i, loss * (double)uc, m, a.item_alpha);
+        sh.lrsum[2 * i + 1] = row_steps(a.usf, user, m.user, i, loss * (double)ic, m, a.user_alpha);
+    }
+    __syncwarp();
+    if (a.item_alpha != 0.0 || a.user_alpha != 0.0) {
+        b0 = __shfl_sync(LFM_FULL, b0, 0);
+        b1 = __shfl_sync(LFM_FULL, b1, 0);
+        double avg = 0.0;
+        avg += b0; avg += b1;
+        for (int i = 0; i < 2 * d; i++) avg += sh.lrsum[i];
+        avg /= (double)((d + 1) * nnz_of(a.usf, user) + (d + 1) * nnz_of(a.itf, item));
+        item_scale *= (1.0 + a.item_alpha * avg);
+        user_scale *= (1.0 + a.user_alpha * avg);
+    }
+    __syncwarp();
+}
+
+// T:652-675 executed by the single replay warp (mid-epoch rescale, T:901-904).
+// Same ownership as everywhere else: lane l touches components l, l+32, ...; lane 0 the biases.
+__device__ void regularize_inline(DevModel& m, double& item_scale, double& user_scale, int lane) {
+    int d = m.d;
+    for (int r = 0; r < m.item.n; r++) {
+        float* w = m.item.w + (size_t)r * d;
+        for (int j = lane; j < d; j += 32) w[j] = (float)((double)w[j] / item_scale);
+        if (lane == 0) m.item.b[r] = (float)((double)m.item.b[r] / item_scale);
+    }
+    for (int r = 0; r < m.user.n; r++) {
+        float* w = m.user.w + (size_t)r * d;
+        for (int j = lane; j < d; j += 32) w[j] = (float)((double)w[j] / user_scale);
+        if (lane == 0) m.user.b[r] = (float)((double)m.user.b[r] / user_scale);
+    }
+    item_scale = 1.0;
+    user_scale = 1.0;
+    __syncwarp();
+}
+
+template <int LOSS>
+__global__ void __launch_bounds__(32, 1) replay_kernel(FitArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    int lane = threadIdx.x;
+    DevModel& m = a.model;
+    int d = m.d;
+    ReplayShared sh;
+    sh.lrsum = (double*)smem;
+    sh.u = (float*)(sh.lrsum + 3 * d);
+    sh.pos = sh.u + (d + 1);
+    sh.neg = sh.pos + (d + 1);
+    sh.pval = sh.neg + (d + 1);
+    sh.pidx = (int*)(sh.pval + (a.nkos > 0 ? a.nkos : 1));
+
+    double item_scale = 1.0, user_scale = 1.0;  // T:254-255
+    uint32_t seed = a.seed;
+    unsigned long long c_pos = 0, c_neg = 0, c_upd = 0, c_rej = 0;
+
+    for (int64_t i = 0; i < a.n; i++) {
+        int row = a.shuffle[i];
+        int user = a.user_ids[row];
+
+        if (LOSS == LOSS_LOGISTIC) {
+            int item = a.item_ids[row];
+            float weight = a.sample_weight[row];
+            gather(a.usf, m.user.w, m.user.b, d, user, user_scale, sh.u, lane);
+            gather(a.itf, m.item.w, m.item.b, d, item, item_scale, sh.pos, lane);
+            double prediction = (double)sigmoid_ref(score(sh.u, sh.pos, d));
+            int y = (a.y[row] <= 0) ? 0 : 1;
+            double loss = (double)weight * (prediction - (double)y);
+            logistic_update(a, loss, user, item, sh, item_scale, user_scale, lane);
+            c_pos++; c_upd++;
+        } else if (LOSS == LOSS_WARP) {
+            int pos_id = a.item_ids[row];
+            if (!(a.y[row] > 0)) continue;
+            float weight = a.sample_weight[row];
+            c_pos++;
+            gather(a.usf, m.user.w, m.user.b, d, user, user_scale, sh.u, lane);
+            gather(a.itf, m.item.w, m.item.b, d, pos_id, item_scale, sh.pos, lane);
+            double pp = (double)score(sh.u, sh.pos, d);
+            int sampled = 0;
+            while (sampled < m.max_sampled) {
+                sampled++;
+                int neg_id = lfm_rand_r(seed) % a.itf.rows;
+                gather(a.itf, m.item.w, m.item.b, d, neg_id, item_scale, sh.neg, lane);
+                double np = (double)score(sh.u, sh.neg, d);
+                c_neg++;
+                if (np > pp - 1) {
+                    if (lfm_bsearch(a.pos.indices, a.pos.indptr[user], a.pos.indptr[user + 1], neg_id)) {
+                        c_rej++;
+                        continue;
+                    }
+                    double loss = (double)weight * a.loss_table[sampled];  // T:881
+                    if (loss > LFM_MAX_LOSS) loss = LFM_MAX_LOSS;
+                    warp_update(a, loss, user, pos_id, neg_id, sh, item_scale, user_scale, lane);
+                    c_upd++;
+                    break;
+                }
+            }
+        } else if (LOSS == LOSS_BPR) {
+            if (!(a.y[row] > 0)) continue;
+            float weight = a.sample_weight[row];
+            int pos_id = a.item_ids[row];
+            int neg_id = 0;
+            for (int64_t j = 0; j < a.n; j++) {  // T:1123-1127
+                neg_id = a.item_ids[lfm_rand_r(seed) % (int)a.n];
+                c_neg++;
+                if (!lfm_bsearch(a.pos.indices, a.pos.indptr[user], a.pos.indptr[user + 1], neg_id)) break;
+                c_rej++;
+            }
+            gather(a.usf, m.user.w, m.user.b, d, user, user_scale, sh.u, lane);
+            gather(a.itf, m.item.w, m.item.b, d, pos_id, item_scale, sh.pos, lane);
+            gather(a.itf, m.item.w, m.item.b, d, neg_id, item_scale, sh.neg, lane);
+            double pp = (double)score(sh.u, sh.pos, d);
+            double np = (double)score(sh.u, sh.neg, d);
+            double loss = (double)weight * (1.0 - (double)sigmoid_ref((float)(pp - np)));
+            warp_update(a, loss, user, pos_id, neg_id, sh, item_scale, user_scale, lane);
+            c_pos++; c_upd++;
+        } else {  // LOSS_KOS, T:957-1062
+            gather(a.usf, m.user.w, m.user.b, d, user, user_scale, sh.u, lane);
+            int ps = a.pos.indptr[user], pe = a.pos.indptr[user + 1];
+            if (pe == ps) continue;
+            c_pos++;
+            int no_pos = (a.nkos < pe - ps) ? a.nkos : (pe - ps);
+            for (int j = 0; j < no_pos; j++) {
+                int sid = a.pos.indices[ps + (lfm_rand_r(seed) % (pe - ps))];  // T:84-90
+                gather(a.itf, m.item.w, m.item.b, d, sid, item_scale, sh.pos, lane);
+                float v = score(sh.u, sh.pos, d);
+                if (lane == 0) { sh.pidx[j] = sid; sh.pval[j] = v; }
+                __syncwarp();
+            }
+            if (lane == 0) {  // stable descending insertion sort == qsort(reverse_pair_compare)
+                for (int x = 1; x < no_pos; x++) {
+                    int ki = sh.pidx[x]; float kv = sh.pval[x];
+                    int y = x - 1;
+                    while (y >= 0 && (sh.pval[y] - kv) < 0) {
+                        sh.pidx[y + 1] = sh.pidx[y]; sh.pval[y + 1] = sh.pval[y]; y--;
+                    }
+                    sh.pidx[y + 1] = ki; sh.pval[y + 1] = kv;
+                }
+            }
+            __syncwarp();
+            int sel = ((a.k < no_pos) ? a.k : no_pos) - 1;
+            int pos_id = sh.pidx[sel];
+            double pp = (double)sh.pval[sel];
+            __syncwarp();
+            gather(a.itf, m.item.w, m.item.b, d, pos_id, item_scale, sh.pos, lane);
+            int sampled = 0;
+            while (sampled < m.max_sampled) {
+                sampled++;
+                int neg_id = lfm_rand_r(seed) % a.itf.rows;
+                gather(a.itf, m.item.w, m.item.b, d, neg_id, item_scale, sh.neg, lane);
+                double np = (double)score(sh.u, sh.neg, d);
+                c_neg++;
+                if (np > pp - 1) {
+                    if (lfm_bsearch(a.pos.indices, ps, pe, neg_id)) { c_rej++; continue; }
+                    double loss = a.loss_table[sampled];  // T:1039: no weight, no max(1, .)
+                    if (loss > LFM_MAX_LOSS) loss = LFM_MAX_LOSS;
+                    warp_update(a, loss, user, pos_id, neg_id, sh, item_scale, user_scale, lane);
+                    c_upd++;
+                    break;
+                }
+            }
+        }
+        if (item_scale > LFM_MAX_REG_SCALE || user_scale > LFM_MAX_REG_SCALE)
+            regularize_inline(m, item_scale, user_scale, lane);
+    }
+    if (lane == 0) {
+        a.scales->item_scale = item_scale;  // final regularize (T:910-912) runs as its own kernel
+        a.scales->user_scale = user_scale;
+        a.counters->positives = c_pos;
+        a.counters->negatives = c_neg;
+        a.counters->updates = c_upd;
+        a.counters->rejected = c_rej;
+    }
+}
+
+// T:652-675 as a full-width sweep; x / 1.0 == x so the launch is skipped by the
+// host when both scales are exactly 1 (alpha == 0).
+__global__ void regularize_kernel(DevModel m, DevScales* scales) {
+    double is = scales->item_scale, us = scales->user_scale;
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t ni = (size_t)m.item.n * m.d, nu = (size_t)m.user.n * m.d;
+    for (size_t i = tid; i < ni; i += stride) m.item.w[i] = (float)((double)m.item.w[i] / is);
+    for (size_t i = tid; i < (size_t)m.item.n; i += stride) m.item.b[i] = (float)((double)m.item.b[i] / is);
+    for (size_t i = tid; i < nu; i += stride) m.user.w[i] = (float)((double)m.user.w[i] / us);
+    for (size_t i = tid; i < (size_t)m.user.n; i += stride) m.user.b[i] = (float)((double)m.user.b[i] / us);
+}
+
+}  // namespace
+
+cudaError_t lfm_launch_replay(int loss, const FitArgs& a, cudaStream_t st) {
+    int d = a.model.d;
+    int nk = a.nkos > 0 ? a.nkos : 1;
+    size_t smem = sizeof(double) * 3 * d + sizeof(float) * 3 * (d + 1) + (sizeof(float) + sizeof(int)) * nk + 16;
+    switch (loss) {
+#define LFM_CASE(L)                                                                              \
+    case L:                                                                                      \
+        if (smem > 48 * 1024)                                                                    \
+            cudaFuncSetAttribute(replay_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                 (int)smem);                                                     \
+        replay_kernel<L><<<1, 32, smem, st>>>(a);                                                \
+        break;
+        LFM_CASE(LOSS_LOGISTIC)
+        LFM_CASE(LOSS_WARP)
+        LFM_CASE(LOSS_BPR)
+        LFM_CASE(LOSS_KOS)
+#undef LFM_CASE
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t lfm_launch_regularize(const DevModel& m, DevScales* scales, cudaStream_t st) {
+    regularize_kernel<<<148 * 8, 256, 0, st>>>(m, scales);
+    return cudaGetLastError();
+}

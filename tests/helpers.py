@@ -160,3 +160,117 @@ def max_rel_diff(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-12))) if a.size else 0.0
+
+
+# ---- golden fixtures (tests/golden/*.npz, generated from the real reference) -------------
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def golden_cases():
+    return sorted(f[len("golden_"):-4] for f in os.listdir(GOLDEN_DIR)
+                  if f.startswith("golden_") and f.endswith(".npz"))
+
+
+class ReplayState(object):
+    """Stands in for numpy RandomState: replays the shuffles / seeds the reference drew."""
+
+    def __init__(self, shuffles, seeds):
+        self.shuffles, self.seeds = list(shuffles), list(seeds)
+
+    def shuffle(self, arr):
+        arr[:] = self.shuffles.pop(0)
+
+    def randint(self, *a, **k):
+        return self.seeds.pop(0).astype(np.int64)
+
+
+def _csr(g, prefix):
+    shape = tuple(int(x) for x in g[prefix + "_shape"])
+    return sp.csr_matrix((g[prefix + "_data"].copy(), g[prefix + "_indices"].copy(),
+                          g[prefix + "_indptr"].copy()), shape=shape)
+
+
+def run_golden(api, name, num_threads=1):
+    """Replay one golden case through `api`; returns (outputs, golden) dicts."""
+    g = np.load(os.path.join(GOLDEN_DIR, "golden_%s.npz" % name))
+    hy = g["hyper"]
+    hp = Hyper(d=int(hy[0]), schedule="adadelta" if hy[1] else "adagrad", lr=float(hy[2]),
+               rho=float(hy[3]), eps=float(hy[4]), max_sampled=int(hy[5]), item_alpha=float(hy[6]),
+               user_alpha=float(hy[6]), k=int(hy[7]), n=int(hy[8]))
+    loss = str(g["loss"])
+    shape = tuple(int(x) for x in g["shape"])
+    inter = sp.coo_matrix((g["data"].copy(), (g["row"].copy(), g["col"].copy())), shape=shape)
+    itf, usf = _csr(g, "itf"), _csr(g, "usf")
+    sw = g["sample_weight"].copy() if "sample_weight" in g.files else None
+    arrays = {k: g["init_" + k].copy() for k in MODEL_ARRAYS}
+    rs = ReplayState(g["shuffles"], g["seeds"])
+    for _ in range(int(hy[9])):
+        run_epoch(api, loss, inter, arrays, hp, rs, itf, usf, sw, num_threads=num_threads)
+    out = {"final_" + k: v for k, v in arrays.items()}
+    # scoring runs on the GOLDEN final state so that each function is pinned on its own
+    gold_arrays = {k: g["final_" + k].copy() for k in MODEL_ARRAYS}
+    h = holder(api, gold_arrays, hp)
+    pred = np.empty(len(g["pred_users"]), dtype=np.float32)
+    api.predict_lightfm(api.CSRMatrix(itf), api.CSRMatrix(usf), g["pred_users"].copy(),
+                        g["pred_items"].copy(), pred, h, 1)
+    out["pred"] = pred
+    test, train = _csr(g, "test"), _csr(g, "train")
+    ranks = np.zeros_like(test.data)
+    api.predict_ranks(api.CSRMatrix(itf), api.CSRMatrix(usf), api.CSRMatrix(test),
+                      api.CSRMatrix(train), ranks, h, 1)
+    out["ranks"] = ranks.copy()
+    auc = np.zeros(test.shape[0], dtype=np.float32)
+    rk = sp.csr_matrix((g["ranks"].copy(), test.indices, test.indptr), shape=test.shape)
+    api.calculate_auc_from_rank(api.CSRMatrix(rk), g["num_train_positives"].copy(), rk.data, auc, 1)
+    out["auc"], out["ranks_sorted"] = auc, rk.data.copy()
+    return out, g
+
+
+def planted_interactions(n_users, n_items, per_user, seed, rank=4, temperature=1.5):
+    """Interactions with learnable low-rank structure (for statistical parity tests)."""
+    rng = np.random.default_rng(seed)
+    ul = rng.normal(size=(n_users, rank))
+    il = rng.normal(size=(n_items, rank))
+    pop = rng.normal(size=n_items) * 0.5
+    scores = temperature * (ul @ il.T) + pop[None, :]
+    g = rng.gumbel(size=scores.shape)
+    top = np.argsort(-(scores + g), axis=1)[:, :per_user]
+    rows = np.repeat(np.arange(n_users), per_user).astype(np.int32)
+    cols = top.ravel().astype(np.int32)
+    return sp.coo_matrix((np.ones(rows.size, np.float32), (rows, cols)), shape=(n_users, n_items))
+
+
+def split(inter, seed, frac=0.8):
+    rs = np.random.RandomState(seed)
+    order = np.arange(inter.nnz)
+    rs.shuffle(order)
+    cut = int(frac * inter.nnz)
+    mk = lambda ix: sp.coo_matrix((inter.data[ix], (inter.row[ix], inter.col[ix])), shape=inter.shape)
+    return mk(order[:cut]), mk(order[cut:])
+
+
+def eval_arrays(arrays, d, train, test, k=10):
+    """Held-out precision@k and AUC of a weight set, computed in numpy (identity features)."""
+    scores = arrays["user_embeddings"].astype(np.float64) @ arrays["item_embeddings"].astype(np.float64).T
+    scores += arrays["user_biases"][:, None] + arrays["item_biases"][None, :]
+    tr = train.tocsr()
+    te = test.tocsr()
+    precs, aucs = [], []
+    for u in range(te.shape[0]):
+        t = te[u].indices
+        if len(t) == 0:
+            continue
+        s = scores[u].copy()
+        s[tr[u].indices] = -np.inf
+        order = np.argsort(-s)
+        topk = set(order[:k].tolist())
+        precs.append(len(topk & set(t.tolist())) / k)
+        neg = np.ones(len(s), bool)
+        neg[tr[u].indices] = False
+        neg[t] = False
+        if neg.sum() == 0:
+            continue
+        ns = np.sort(s[neg])
+        rank_below = np.searchsorted(ns, s[t], side="left")
+        aucs.append(float(np.mean(rank_below / neg.sum())))
+    return float(np.mean(precs)), float(np.mean(aucs))

@@ -1,0 +1,108 @@
+"""GPU: public-API behaviour of LightFM end to end (restates the offline-capable cases of the
+reference's tests/test_api.py and the state/RNG invariants of tests/test_movielens.py)."""
+import pickle
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import helpers as H
+from lightfm_b200 import LightFM
+
+pytestmark = pytest.mark.gpu
+
+
+def test_empty_matrix():  # tests/test_api.py:10-17
+    LightFM().fit(sp.coo_matrix((20, 30), dtype=np.int32))
+
+
+@pytest.mark.parametrize("fmt", ("coo", "csr", "csc", "lil", "dok"))
+@pytest.mark.parametrize("dtype", (np.int32, np.int64, np.float32, np.float64))
+def test_matrix_types(fmt, dtype):  # tests/test_api.py:20-54
+    rng = np.random.RandomState(0)
+    dense = (rng.rand(12, 9) > 0.6).astype(dtype)
+    train = getattr(sp, fmt + "_matrix")(dense)
+    uf = getattr(sp, fmt + "_matrix")(np.eye(12, dtype=dtype))
+    itf = getattr(sp, fmt + "_matrix")(np.eye(9, dtype=dtype))
+    w = sp.coo_matrix(train, dtype=dtype)
+    model = LightFM(no_components=4)
+    model.fit(train, user_features=uf, item_features=itf, sample_weight=w if dense.any() else None)
+    model.predict(np.arange(5, dtype=np.int32), np.arange(5, dtype=np.int32),
+                  user_features=uf, item_features=itf)
+    model.predict_rank(train, user_features=uf, item_features=itf, check_intersections=False)
+
+
+@pytest.mark.parametrize("loss", ("warp", "bpr", "warp-kos"))
+def test_coo_with_duplicate_entries(loss):  # tests/test_api.py:57-74
+    rows = np.array([0, 0, 0, 1, 1, 2, 2, 2], dtype=np.int32)
+    cols = np.array([0, 0, 1, 1, 1, 2, 0, 0], dtype=np.int32)
+    mat = sp.coo_matrix((np.ones(8, np.float32), (rows, cols)), shape=(3, 4))
+    for nt in (1, 2):
+        LightFM(loss=loss, no_components=4).fit(mat, epochs=2, num_threads=nt)
+
+
+def test_return_self_and_feature_shape_errors():  # tests/test_api.py:121-168
+    train = sp.coo_matrix((np.ones(3, np.float32), ([0, 1, 2], [0, 1, 2])), shape=(3, 3))
+    model = LightFM(no_components=4)
+    assert model.fit_partial(train) is model
+    assert model.fit(train) is model
+    with pytest.raises(ValueError):
+        model.fit_partial(train, item_features=sp.csr_matrix(np.ones((3, 5), np.float32)))
+    with pytest.raises(ValueError):
+        model.predict(np.arange(3), np.arange(3), user_features=sp.csr_matrix(np.ones((3, 7), np.float32)))
+
+
+def test_overflow_divergence_raises():  # tests/test_api.py:285-294
+    rng = np.random.RandomState(0)
+    train = sp.coo_matrix((rng.rand(40, 30) > 0.5).astype(np.float32) * 1e9)
+    feats = sp.csr_matrix(rng.rand(30, 10).astype(np.float32) * 1e9)
+    for nt in (1, 4):
+        with pytest.raises(ValueError):
+            LightFM(loss="logistic", learning_rate=1e6, no_components=4).fit(
+                train, item_features=feats, epochs=5, num_threads=nt)
+
+
+def test_warp_few_items_stays_finite():  # tests/test_api.py:374-382
+    train = sp.coo_matrix((np.ones(4, np.float32), ([0, 1, 2, 3], [0, 1, 0, 1])), shape=(4, 2))
+    for nt in (1, 4):
+        model = LightFM(loss="warp", max_sampled=10, no_components=4).fit(train, epochs=3, num_threads=nt)
+        assert np.isfinite(model.item_embeddings).all() and np.isfinite(model.user_embeddings).all()
+
+
+def test_state_reset_resume_and_pickle():  # tests/test_movielens.py:387-412,463-472
+    train = H.synthetic_interactions(80, 60, 1500, 2)
+    model = LightFM(loss="warp", no_components=8, random_state=3)
+    model.fit(train, epochs=2)
+    again = pickle.loads(pickle.dumps(model))
+    for k in H.MODEL_ARRAYS:
+        assert np.array_equal(getattr(model, k), getattr(again, k))
+    # resume: 1 + 1 epochs via fit_partial == 2 epochs in one call (same RNG stream)
+    a = LightFM(loss="warp", no_components=8, random_state=3)
+    a.fit_partial(train, epochs=1)
+    a.fit_partial(train, epochs=1)
+    assert np.array_equal(a.item_embeddings, model.item_embeddings)
+    # fit() discards the previous state
+    model.fit(train, epochs=0)
+    assert np.all(model.item_bias_gradients == 1)
+
+
+def test_random_state_advances_each_epoch():  # tests/test_movielens.py:669-682
+    train = H.synthetic_interactions(80, 60, 1500, 2)
+    for nt in (1, 4):
+        model = LightFM(loss="warp", no_components=8, random_state=3)
+        states = []
+        for _ in range(3):
+            model.fit_partial(train, epochs=1, num_threads=nt)
+            states.append(model.random_state.get_state()[1].copy())
+        assert not np.array_equal(states[0], states[1])
+        assert not np.array_equal(states[1], states[2])
+
+
+def test_user_mutation_between_calls_is_respected():
+    train = H.synthetic_interactions(80, 60, 1500, 2)
+    model = LightFM(loss="warp", no_components=8, random_state=3).fit(train, epochs=1)
+    model.item_biases *= 0.0
+    model.item_biases += 5.0
+    p = model.predict(0, np.arange(60, dtype=np.int32))
+    emb = model.user_embeddings[0] @ model.item_embeddings.T + model.user_biases[0] + 5.0
+    assert np.allclose(p, emb, atol=1e-5)

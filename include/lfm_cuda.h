@@ -199,6 +199,14 @@ int lfm_plan_create(lfm_plan **out, int32_t loss, const lfm_csr *item_features,
 int lfm_plan_epoch(lfm_plan *plan, const int32_t *shuffle_indices, uint32_t seed,
                    int32_t num_threads, lfm_counters *counters);
 int lfm_plan_download(lfm_plan *plan, lfm_model *model);
+/* Device address and element count of one resident state array (for the caller's own
+ * collectives): which = 0..5 item {w,g,m,b,bg,bm}, 6..11 user {w,g,m,b,bg,bm}. */
+int lfm_plan_table(lfm_plan *plan, int32_t which, void **dev_ptr, int64_t *count);
+/* Device-side version of the per-epoch divergence check (lightfm.py:447-464): *all_finite = 1
+ * when every embedding and bias is finite. */
+int lfm_plan_check_finite(lfm_plan *plan, int32_t *all_finite);
+/* Item-sharded runs: keep the global catalogue size in the WARP rank estimate (T:881). */
+int lfm_plan_set_global_items(lfm_plan *plan, int32_t n_items_global);
 int lfm_plan_destroy(lfm_plan *plan);
 
 #ifdef __cplusplus

@@ -60,6 +60,12 @@ def device_count():
     return _lib.lfm_device_count()
 
 
+def resolves_to_hogwild(num_threads):
+    """True when a fit call with this num_threads runs the throughput kernels."""
+    mode = _lib.lfm_get_mode()
+    return mode == 2 or (mode == 0 and num_threads > 1)
+
+
 def set_fast_path(enabled):
     """Testing hook: disable the specialised hogwild kernels (generic ones run instead)."""
     fn = _lib.lfm_set_fast_path
@@ -68,10 +74,20 @@ def set_fast_path(enabled):
     return fn(int(bool(enabled)))
 
 
+def set_inflight_divisor(divisor):
+    """Hogwild launches keep at most max(64, n / divisor) interactions in flight (default 128)."""
+    fn = _lib.lfm_set_inflight_divisor
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_int]
+    return fn(int(divisor))
+
+
 def release_cache():
     _check(_lib.lfm_release_cache())
 
 
+if os.environ.get("LIGHTFM_CUDA_INFLIGHT_DIVISOR"):
+    set_inflight_divisor(int(os.environ["LIGHTFM_CUDA_INFLIGHT_DIVISOR"]))
 if os.environ.get("LIGHTFM_CUDA_MODE"):
     set_mode(os.environ["LIGHTFM_CUDA_MODE"].lower())
 
@@ -127,6 +143,20 @@ class ResidentPlan(object):
 
     def download(self):
         _check(_lib.lfm_plan_download(self._handle, self._lightfm.ptr))
+
+    def all_finite(self):
+        ok = ctypes.c_int32(0)
+        _check(_lib.lfm_plan_check_finite(self._handle, ctypes.byref(ok)))
+        return bool(ok.value)
+
+    def set_global_items(self, n_items_global):
+        _check(_lib.lfm_plan_set_global_items(self._handle, int(n_items_global)))
+
+    def table(self, which):
+        """(device pointer, element count) of resident state array `which` (see lfm_plan_table)."""
+        ptr, cnt = ctypes.c_void_p(), ctypes.c_int64()
+        _check(_lib.lfm_plan_table(self._handle, int(which), ctypes.byref(ptr), ctypes.byref(cnt)))
+        return ptr.value, cnt.value
 
     def close(self):
         if self._handle:

@@ -368,6 +368,24 @@ __global__ void regularize_log_kernel(DevModel m, DevScales* scales) {
 }
 __global__ void reset_scales_kernel(DevScales* s) { s->item_scale = 0.0; s->user_scale = 0.0; }
 
+}  // namespace
+// Hogwild relies on collisions being rare: the interactions in flight at any moment must be a
+// small fraction of the epoch, or every update is computed from a state that is a whole epoch
+// stale (the reference's OpenMP loop has num_threads <= ~100 in flight).  The grid is therefore
+// capped at max(64, n / divisor) concurrent interactions; a full B200 wave (~4.7k warps) is
+// reached from ~600k interactions per launch.
+static int g_inflight_divisor = 128;
+extern "C" int lfm_set_inflight_divisor(int divisor) {
+    int old = g_inflight_divisor;
+    if (divisor >= 1) g_inflight_divisor = divisor;
+    return old;
+}
+static int64_t lfm_inflight_cap(int64_t count) {
+    int64_t cap = count / g_inflight_divisor;
+    return cap < 64 ? 64 : cap;
+}
+namespace {
+
 template <int LOSS, int KPL>
 cudaError_t launch_generic(const FitArgs& a, const Tuple* tuples, int64_t begin, int64_t count,
                            cudaStream_t st) {
@@ -380,6 +398,8 @@ cudaError_t launch_generic(const FitArgs& a, const Tuple* tuples, int64_t begin,
     int64_t blocks = (warps_needed * 32 + block - 1) / block;
     int64_t cap = 148 * 8;
     if (blocks > cap) blocks = cap;
+    int64_t fl = (lfm_inflight_cap(count) + 7) / 8;
+    if (blocks > fl) blocks = fl;
     if (blocks < 1) blocks = 1;
     if (a.model.adadelta) {
         if (reg) hogwild_kernel<LOSS, KPL, true, true><<<(int)blocks, block, 0, st>>>(b, tp);

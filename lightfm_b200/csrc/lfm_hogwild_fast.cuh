@@ -297,7 +297,7 @@ struct FastGrid {
     int blocks, threads;
 };
 template <typename K>
-FastGrid fast_grid(K kernel, int64_t warps_wanted) {
+FastGrid fast_grid(K kernel, int64_t warps_wanted, int64_t warps_cap) {
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0);
     if (per_sm < 1) per_sm = 1;
@@ -307,6 +307,8 @@ FastGrid fast_grid(K kernel, int64_t warps_wanted) {
     int64_t blocks = (int64_t)sms * per_sm;  // one full wave of resident CTAs (persistent warps)
     int64_t need = (warps_wanted + 7) / 8;
     if (blocks > need) blocks = need;
+    int64_t cap = (warps_cap + 7) / 8;
+    if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     FastGrid g = {(int)blocks, 256};
     return g;
@@ -319,11 +321,12 @@ cudaError_t launch_fast(const FitArgs& a, const Tuple* tuples, int64_t begin, in
     b.n = count;
     const Tuple* tp = tuples + begin;
     if constexpr (LOSS == LOSS_WARP || LOSS == LOSS_KOS) {
-        FastGrid g = fast_grid(fast_rank_kernel<LOSS, LPR>, count);
+        FastGrid g = fast_grid(fast_rank_kernel<LOSS, LPR>, count, lfm_inflight_cap(count));
         fast_rank_kernel<LOSS, LPR><<<g.blocks, g.threads, 0, st>>>(b, tp);
     } else {
         constexpr int NS = 32 / LPR;
-        FastGrid g = fast_grid(fast_pair_kernel<LOSS, LPR>, (count + NS - 1) / NS);
+        FastGrid g = fast_grid(fast_pair_kernel<LOSS, LPR>, (count + NS - 1) / NS,
+                               (lfm_inflight_cap(count) + NS - 1) / NS);
         fast_pair_kernel<LOSS, LPR><<<g.blocks, g.threads, 0, st>>>(b, tp);
     }
     return cudaGetLastError();

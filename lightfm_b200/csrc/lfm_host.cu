@@ -777,7 +777,75 @@ extern "C" int lfm_plan_download(lfm_plan* p, lfm_model* model) {
     return LFM_OK;
 }
 
-// Device-side divergence check (lightfm.py:447-464): 1 if every parameter is finite.
+// Divergence check on the device (lightfm.py:447-464 does isfinite(sum(x)) on the host after every
+// epoch; with resident state that would cost a full model download per epoch).
+__global__ void finite_kernel(const float* a, size_t na, const float* b, size_t nb, const float* c,
+                              size_t nc, const float* d, size_t nd, int32_t* flag) {
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    bool bad = false;
+    for (size_t i = tid; i < na; i += stride) bad |= !isfinite(a[i]);
+    for (size_t i = tid; i < nb; i += stride) bad |= !isfinite(b[i]);
+    for (size_t i = tid; i < nc; i += stride) bad |= !isfinite(c[i]);
+    for (size_t i = tid; i < nd; i += stride) bad |= !isfinite(d[i]);
+    if (bad) *flag = 0;
+}
+
+extern "C" int lfm_plan_check_finite(lfm_plan* p, int32_t* all_finite) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (!p || !all_finite) return fail(LFM_ERR_ARG, "null argument");
+    g_cur = &p->arena;
+    struct Restore { ~Restore() { g_cur = &g_arena; } } restore;
+    void* f = nullptr;
+    int rc = arena_get("finite.flag", sizeof(int32_t), &f);
+    if (rc != LFM_OK) return rc;
+    const DevModel& m = p->st.a.model;
+    int32_t one = 1, h = 0;
+    CU(cudaMemcpyAsync(f, &one, sizeof(one), cudaMemcpyHostToDevice, g_stream));
+    finite_kernel<<<148 * 8, 256, 0, g_stream>>>(m.item.w, (size_t)m.item.n * m.d, m.item.b, (size_t)m.item.n,
+                                                  m.user.w, (size_t)m.user.n * m.d, m.user.b,
+                                                  (size_t)m.user.n, (int32_t*)f);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(&h, f, sizeof(h), cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    *all_finite = h;
+    return LFM_OK;
+}
+
+// Item-sharded multi-GPU runs: negatives are drawn from the local shard but the
+// WARP rank estimate floor((n_items - 1) / sampled) keeps the GLOBAL catalogue size.
+extern "C" int lfm_plan_set_global_items(lfm_plan* p, int32_t n_items_global) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (!p || n_items_global < 1) return fail(LFM_ERR_ARG, "bad argument");
+    Staged& st = p->st;
+    int ms = st.a.model.max_sampled > 0 ? st.a.model.max_sampled : 0;
+    st.table.assign((size_t)ms + 1, 0.0);
+    for (int s = 1; s <= ms; s++) {
+        double fl = floor((double)((n_items_global - 1) / s));
+        st.table[s] = (p->loss == LOSS_KOS) ? log(fl) : log(fl > 1.0 ? fl : 1.0);
+    }
+    CU(cudaMemcpyAsync((void*)st.a.loss_table, st.table.data(), sizeof(double) * st.table.size(),
+                       cudaMemcpyHostToDevice, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    return LFM_OK;
+}
+
+// Device address + element count of one resident state array, for callers that run their
+// own collectives on it (multi-GPU delta all-reduce).  which: 0..5 item {w,g,m,b,bg,bm},
+// 6..11 user {w,g,m,b,bg,bm}.  Arrays the plan does not hold (momentum under adagrad) give NULL.
+extern "C" int lfm_plan_table(lfm_plan* p, int32_t which, void** dev_ptr, int64_t* count) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (!p || !dev_ptr || !count) return fail(LFM_ERR_ARG, "null argument");
+    if (which < 0 || which > 11) return fail(LFM_ERR_ARG, "bad table index %d", which);
+    const DevModel& dm = p->st.a.model;
+    const DevTable& t = which < 6 ? dm.item : dm.user;
+    float* ptrs[6] = {t.w, t.g, t.m, t.b, t.bg, t.bm};
+    int k = which % 6;
+    *dev_ptr = ptrs[k];
+    *count = ptrs[k] ? (k < 3 ? (int64_t)t.n * dm.d : (int64_t)t.n) : 0;
+    return LFM_OK;
+}
+
 extern "C" int lfm_plan_destroy(lfm_plan* p) {
     std::lock_guard<std::mutex> lock(g_mu);
     if (!p) return LFM_OK;

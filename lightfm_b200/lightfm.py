@@ -250,11 +250,47 @@ class LightFM(object):
         if num_threads < 1:
             raise ValueError("Number of threads must be 1 or larger.")
 
+        if epochs > 0 and _native.resolves_to_hogwild(num_threads) and self._resident_ok():
+            self._run_epochs_resident(item_features, user_features, interactions,
+                                      sample_weight_data, num_threads, epochs, verbose)
+            return self
+
         for _ in self._progress(epochs, verbose=verbose):
             self._run_epoch(item_features, user_features, interactions, sample_weight_data,
                             num_threads, self.loss)
             self._check_finite()
         return self
+
+    def _resident_ok(self):
+        # k-OS with n > 32 falls back to replay inside the library; keep the per-epoch path there
+        return self.no_components <= 256 and not (self.loss == "warp-kos" and self.n > 32)
+
+    def _run_epochs_resident(self, item_features, user_features, interactions, sample_weight,
+                             num_threads, epochs, verbose):
+        """Throughput mode: upload the problem once, run all epochs on the device
+        (SURVEY 8(f) row 1).  The reference re-builds the positives CSR, re-shuffles on the host
+        and re-crosses the boundary with every array once per epoch (L:668-759); here each epoch
+        consumes ONE ``random_state.randint`` draw (the key of the device-side permutation and
+        of the Philox negative sampler), so the caller's RandomState still advances every epoch.
+        The numpy state arrays are written back once at the end (or before raising)."""
+        pairwise = self.loss in ("warp", "bpr", "warp-kos")
+        positives = _native.CSRMatrix(self._positives_lookup(interactions)) if pairwise else None
+        kos = self.loss == "warp-kos"
+        plan = _native.ResidentPlan(
+            self.loss, _native.CSRMatrix(item_features), _native.CSRMatrix(user_features), positives,
+            interactions.row, None if kos else interactions.col, None if kos else interactions.data,
+            None if kos else sample_weight, self._get_lightfm_data(), self.item_alpha,
+            self.user_alpha, self.k, self.n)
+        try:
+            for _ in self._progress(epochs, verbose=verbose):
+                seed = self.random_state.randint(0, np.iinfo(np.int32).max)
+                plan.epoch(seed, num_threads=max(2, num_threads))
+                if not plan.all_finite():
+                    break
+        finally:
+            plan.download()
+            plan.close()
+        self._check_finite()
 
     def _run_epoch(self, item_features, user_features, interactions, sample_weight,
                    num_threads, loss):

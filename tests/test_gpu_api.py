@@ -34,9 +34,12 @@ def test_matrix_types(fmt, dtype):  # tests/test_api.py:20-54
 
 @pytest.mark.parametrize("loss", ("warp", "bpr", "warp-kos"))
 def test_coo_with_duplicate_entries(loss):  # tests/test_api.py:57-74
-    rows = np.array([0, 0, 0, 1, 1, 2, 2, 2], dtype=np.int32)
-    cols = np.array([0, 0, 1, 1, 1, 2, 0, 0], dtype=np.int32)
-    mat = sp.coo_matrix((np.ones(8, np.float32), (rows, cols)), shape=(3, 4))
+    rng = np.random.RandomState(0)
+    rows = rng.randint(0, 40, 300).astype(np.int32)
+    cols = rng.randint(0, 30, 300).astype(np.int32)
+    rows = np.concatenate([rows, rows[:100]])  # duplicate COO entries (lightfm issue #117)
+    cols = np.concatenate([cols, cols[:100]])
+    mat = sp.coo_matrix((np.ones(400, np.float32), (rows, cols)), shape=(40, 30))
     for nt in (1, 2):
         LightFM(loss=loss, no_components=4).fit(mat, epochs=2, num_threads=nt)
 

@@ -82,12 +82,22 @@ def set_inflight_divisor(divisor):
     return fn(int(divisor))
 
 
+def set_tuning(variant):
+    """WARP fast-path kernel variant: 0 = v1, 1/2/3 = pipelined v2 at 4/5/6 CTAs per SM."""
+    fn = _lib.lfm_set_tuning
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_int]
+    return fn(int(variant))
+
+
 def release_cache():
     _check(_lib.lfm_release_cache())
 
 
 if os.environ.get("LIGHTFM_CUDA_INFLIGHT_DIVISOR"):
     set_inflight_divisor(int(os.environ["LIGHTFM_CUDA_INFLIGHT_DIVISOR"]))
+if os.environ.get("LIGHTFM_CUDA_TUNING"):
+    set_tuning(int(os.environ["LIGHTFM_CUDA_TUNING"]))
 if os.environ.get("LIGHTFM_CUDA_MODE"):
     set_mode(os.environ["LIGHTFM_CUDA_MODE"].lower())
 

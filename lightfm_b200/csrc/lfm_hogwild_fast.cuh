@@ -28,6 +28,13 @@ __device__ __forceinline__ void red_add(float* addr, float a) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
 }
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg((const float4*)p); }
+// G >= 1 under adagrad (starts at 1, only grows): no denormals, so the bare approximation is safe
+__device__ __forceinline__ float rsqrt_ftz(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 
 template <int LPR>
 __device__ __forceinline__ float slot_sum(float v) {
@@ -43,13 +50,13 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
 __device__ __forceinline__ void adagrad_row4(float* w, float* G, float lr, float gx, float gy,
                                              float gz, float gw) {
     float4 g0 = ldcg4(G);
-    red_add_v4(w, -lr * rsqrtf(g0.x) * gx, -lr * rsqrtf(g0.y) * gy, -lr * rsqrtf(g0.z) * gz,
-               -lr * rsqrtf(g0.w) * gw);
+    red_add_v4(w, -lr * rsqrt_ftz(g0.x) * gx, -lr * rsqrt_ftz(g0.y) * gy, -lr * rsqrt_ftz(g0.z) * gz,
+               -lr * rsqrt_ftz(g0.w) * gw);
     red_add_v4(G, gx * gx, gy * gy, gz * gz, gw * gw);
 }
 __device__ __forceinline__ void adagrad_scalar(float* b, float* G, float lr, float g) {
     float g0 = __ldcg(G);
-    red_add(b, -lr * rsqrtf(g0) * g);
+    red_add(b, -lr * rsqrt_ftz(g0) * g);
     red_add(G, g * g);
 }
 
@@ -198,6 +205,484 @@ __global__ void __launch_bounds__(256) fast_rank_kernel(FitArgs a, const Tuple* 
     }
 }
 
+// ---- WARP, software-pipelined (v2) ---------------------------------------------
+// Same algorithm as fast_rank_kernel<LOSS_WARP>, restructured to shorten the per-interaction
+// chain of dependent L2 round trips (ncu r1: long-scoreboard stalls dominate, DRAM at 9%):
+//   * while interaction i is in its sampling loop, the tuple of interaction i+1 is loaded;
+//   * before interaction i's update, cp.async (LDGSTS, .cg = L2-coherent) stages interaction
+//     i+1's user row, positive row and their two accumulator rows into shared memory
+//     (double-buffered, 4 rows x d floats per buffer per warp) and its scalars (biases, CSR
+//     row bounds) into registers, so they arrive during the update / loop turn-around;
+//   * the accumulator rows of user and positive are thereby already on chip at update time;
+//     only the sampled negative's accumulator row is fetched on the critical path.
+// Philox4x32-7 (BigCrush-clean per Salmon et al.) with all four outputs consumed;
+// rsqrt.approx.ftz (G >= 1 under adagrad, no denormals); 32-bit per-warp counters.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ Philox4 philox7(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                           uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 7; r++) {
+        uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+        uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    Philox4 o = {c0, c1, c2, c3};
+    return o;
+}
+
+__device__ __forceinline__ void adagrad_row4_g(float* w, float* G, const float4& g0, float lr,
+                                               float gx, float gy, float gz, float gw) {
+    red_add_v4(w, -lr * rsqrt_ftz(g0.x) * gx, -lr * rsqrt_ftz(g0.y) * gy, -lr * rsqrt_ftz(g0.z) * gz,
+               -lr * rsqrt_ftz(g0.w) * gw);
+    red_add_v4(G, gx * gx, gy * gy, gz * gz, gw * gw);
+}
+
+struct TupleScalars {
+    float ub, pb;    // user / positive-item bias
+    float ubg, pbg;  // their Adagrad accumulators (consumed by lanes 2 / 0 at update time)
+    int ps, pe;      // bounds of the user's row in the positives CSR
+    int probe;       // lane's first-level probe of that row (key independent, see warp_member2)
+};
+
+// Membership of `key` in the sorted row idx[lo, hi) with the first level already in registers.
+// Level 1 (prefetched by the caller, independent of the key):
+//     len <= 32 : probe = idx[lo + lane]                     (the whole row)
+//     len  > 32 : probe = idx[lo + (len * lane >> 5)]        (32 pivots, pivot 0 = first element)
+// so a violating negative costs zero (short rows) or one dependent L2 round trip per further
+// factor 32 of row length, instead of log2(len) as in the reference's bsearch (T:270-284).
+__device__ __forceinline__ int probe_index(int lo, int hi, int lane) {
+    const int len = hi - lo;
+    if (len <= 32) return lane < len ? lo + lane : -1;
+    return lo + (int)(((unsigned long long)(unsigned)len * (unsigned)lane) >> 5);
+}
+__device__ __forceinline__ bool warp_member2(const int32_t* __restrict__ idx, int lo, int hi, int probe,
+                                             int key, int lane) {
+    int len = hi - lo;
+    if (len <= 32) return __any_sync(LFM_FULL, lane < len && probe == key);
+    int v = probe;
+    while (true) {
+        // pivots p_l = lo + (len*l >> 5), l = 0..31, p_0 = lo; c = number of pivots <= key
+        const unsigned le = __ballot_sync(LFM_FULL, v <= key);
+        const int c = __popc(le);
+        if (c == 0) return false;  // key < first element
+        if (__any_sync(LFM_FULL, v == key)) return true;
+        const int nlo = lo + (int)(((unsigned long long)(unsigned)len * (unsigned)(c - 1)) >> 5);
+        const int nhi = c == 32 ? hi : lo + (int)(((unsigned long long)(unsigned)len * (unsigned)c) >> 5);
+        lo = nlo + 1;  // idx[nlo] != key (checked above)
+        hi = nhi;
+        len = hi - lo;
+        if (len <= 0) return false;
+        if (len <= 32) {
+            v = lane < len ? __ldg(idx + lo + lane) : -1;
+            return __any_sync(LFM_FULL, lane < len && v == key);
+        }
+        v = __ldg(idx + lo + (int)(((unsigned long long)(unsigned)len * (unsigned)lane) >> 5));
+    }
+}
+
+template <int LPR, int MINB>
+__global__ void __launch_bounds__(256, MINB) fast_warp_v2_kernel(FitArgs a, const Tuple* __restrict__ tuples) {
+    constexpr int D = 4 * LPR;
+    constexpr int NS = 32 / LPR;
+    constexpr int ROWF = D;               // floats per staged row
+    constexpr int BUFF = 4 * ROWF;        // u, p, Gu, Gp
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int sub = lane % LPR, slot = lane / LPR;
+    float* wbuf = smem + (size_t)wib * 2 * BUFF;
+    const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+    const int n_tuples = (int)a.n;  // no_examples < 2^31 (checked by the host layer)
+    const DevModel& m = a.model;
+    const float lr = m.lr;
+    const int n_items = a.itf.rows;
+    const int max_sampled = m.max_sampled;
+    unsigned c_pos = 0, c_neg = 0, c_upd = 0, c_rej = 0;
+
+    // stage the four rows of one interaction: 4*LPR chunks of 16 B spread over the 32 lanes
+    auto stage = [&](const Tuple& tp, float* buf, TupleScalars& sc) {
+        if (tp.user < 0) return;
+#pragma unroll
+        for (int c = lane; c < 4 * LPR; c += 32) {
+            const int row = c / LPR, ch = c % LPR;  // row: 0 user w, 1 item w, 2 user g, 3 item g
+            const float* base = (row & 2) ? ((row & 1) ? m.item.g : m.user.g)
+                                          : ((row & 1) ? m.item.w : m.user.w);
+            const int id = (row & 1) ? tp.item : tp.user;
+            cp_async16(buf + row * ROWF + ch * 4, base + (size_t)id * D + ch * 4);
+        }
+        sc.ub = __ldcg(m.user.b + tp.user);
+        sc.pb = __ldcg(m.item.b + tp.item);
+        sc.ubg = __ldcg(m.user.bg + tp.user);
+        sc.pbg = __ldcg(m.item.bg + tp.item);
+        sc.ps = __ldg(a.pos.indptr + tp.user);
+        sc.pe = __ldg(a.pos.indptr + tp.user + 1);
+        const int pi = probe_index(sc.ps, sc.pe, lane);
+        sc.probe = pi >= 0 ? __ldg(a.pos.indices + pi) : -1;
+    };
+
+    int t = warp;
+    Tuple cur = {-1, 0, 0.0f, 0.0f};
+    TupleScalars cs = {0.f, 0.f, 0.f, 0.f, 0, 0, -1};
+    if (t < n_tuples) cur = tuples[t];
+    stage(cur, wbuf, cs);
+    cp_async_commit();
+    int flip = 0;
+
+    for (; t < n_tuples; t += nwarps, flip ^= 1) {
+        Tuple nxt = {-1, 0, 0.0f, 0.0f};
+        TupleScalars ns = {0.f, 0.f, 0.f, 0.f, 0, 0, -1};
+        if (t + nwarps < n_tuples && t + nwarps > 0) nxt = tuples[t + nwarps];
+        float* buf = wbuf + flip * BUFF;
+        float* nbuf = wbuf + (flip ^ 1) * BUFF;
+        cp_async_wait_all();
+        __syncwarp();
+        if (cur.user < 0) {
+            stage(nxt, nbuf, ns);
+            cp_async_commit();
+            cur = nxt;
+            cs = ns;
+            continue;
+        }
+        c_pos++;
+        const int user = cur.user, pos_id = cur.item;
+        const float4 u4 = *(const float4*)(buf + 0 * ROWF + sub * 4);
+        float pp;
+        {
+            const float4 p4 = *(const float4*)(buf + 1 * ROWF + sub * 4);
+            pp = slot_sum<LPR>(dot4(u4, p4)) + cs.ub + cs.pb;
+        }
+        // ---- rank sampling, NS speculative candidates per round ----
+        int sampled = 0, neg_id = -1, neg_lane = 0;
+        float loss = 0.0f;
+        float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t ctr = 0;
+        Philox4 r4 = {0u, 0u, 0u, 0u};
+        int have = 0;  // unread 32-bit outputs left in r4 (per slot stream: slot-th lane group)
+        while (sampled < max_sampled && neg_id < 0) {
+            const int nb = min(NS, max_sampled - sampled);
+            // one Philox call yields 4 words; each round consumes NS words (one per slot)
+            uint32_t r;
+            if (NS >= 4) {
+                r4 = philox7((uint32_t)t, 0u, ctr + (slot >> 2), 0u, a.seed, 0x4c464d31u);
+                ctr += NS / 4;
+                r = (slot & 3) == 0 ? r4.x : (slot & 3) == 1 ? r4.y : (slot & 3) == 2 ? r4.z : r4.w;
+            } else {
+                if (have < NS) {
+                    r4 = philox7((uint32_t)t, 0u, ctr++, 0u, a.seed, 0x4c464d31u);
+                    have = 4;
+                }
+                const int idx = (4 - have) + slot;  // NS in {1,2}: words are handed out in order
+                r = idx == 0 ? r4.x : idx == 1 ? r4.y : idx == 2 ? r4.z : r4.w;
+                have -= NS;
+            }
+            const int cand = lfm_bounded(r, (uint32_t)n_items);
+            const bool act = slot < nb;
+            if (act) q4 = ldcg4(m.item.w + (size_t)cand * D + sub * 4);
+            const float qb = act ? __ldcg(m.item.b + cand) : 0.0f;
+            const float np = slot_sum<LPR>(dot4(u4, q4)) + cs.ub + qb;
+            unsigned vm = __ballot_sync(LFM_FULL, act && sub == 0 && np > pp - 1.0f);
+            int consumed = nb;
+            while (vm) {
+                const int first = __ffs(vm) - 1;
+                const int ck = __shfl_sync(LFM_FULL, cand, first);
+                if (warp_member2(a.pos.indices, cs.ps, cs.pe, cs.probe, ck, lane)) {
+                    c_rej++;
+                    vm &= vm - 1;
+                    continue;
+                }
+                const int k = first / LPR;
+                consumed = k + 1;
+                neg_id = ck;
+                neg_lane = first;
+                loss = fminf(cur.weight * (float)a.loss_table[sampled + k + 1], (float)LFM_MAX_LOSS);
+                break;
+            }
+            sampled += consumed;
+            c_neg += consumed;
+        }
+        // ---- prefetch the next interaction while this one updates ----
+        stage(nxt, nbuf, ns);
+        cp_async_commit();
+
+        if (neg_id >= 0) {
+            c_upd++;
+            // the only fetches left on the critical path: the negative's accumulator row and
+            // its bias accumulator -- issued together, before any arithmetic
+            const size_t on = (size_t)neg_id * D + sub * 4;
+            float4 gn = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (NS == 1 || slot == 1 % NS) gn = ldcg4(m.item.g + on);
+            float nbg = 1.0f;
+            if (lane == 1) nbg = __ldcg(m.item.bg + neg_id);
+            float4 n4;
+            n4.x = __shfl_sync(LFM_FULL, q4.x, neg_lane + sub);
+            n4.y = __shfl_sync(LFM_FULL, q4.y, neg_lane + sub);
+            n4.z = __shfl_sync(LFM_FULL, q4.z, neg_lane + sub);
+            n4.w = __shfl_sync(LFM_FULL, q4.w, neg_lane + sub);
+#pragma unroll
+            for (int task = slot; task < 3; task += NS) {
+                if (task == 0) {  // positive item row: gradient -loss * u ; G row already staged
+                    const float4 g0 = *(const float4*)(buf + 3 * ROWF + sub * 4);
+                    size_t o = (size_t)pos_id * D + sub * 4;
+                    adagrad_row4_g(m.item.w + o, m.item.g + o, g0, lr, -loss * u4.x, -loss * u4.y,
+                                   -loss * u4.z, -loss * u4.w);
+                } else if (task == 1) {  // negative item row: +loss * u
+                    adagrad_row4_g(m.item.w + on, m.item.g + on, gn, lr, loss * u4.x, loss * u4.y,
+                                   loss * u4.z, loss * u4.w);
+                } else {  // user row: loss * (neg - pos)
+                    const float4 g0 = *(const float4*)(buf + 2 * ROWF + sub * 4);
+                    const float4 p4 = *(const float4*)(buf + 1 * ROWF + sub * 4);
+                    size_t o = (size_t)user * D + sub * 4;
+                    adagrad_row4_g(m.user.w + o, m.user.g + o, g0, lr, loss * (n4.x - p4.x),
+                                   loss * (n4.y - p4.y), loss * (n4.z - p4.z), loss * (n4.w - p4.w));
+                }
+            }
+            if (lane < 3) {  // biases: lane 0 positive (-loss), lane 1 negative (+loss), lane 2 user (+loss)
+                float* b = lane == 0 ? m.item.b + pos_id : lane == 1 ? m.item.b + neg_id : m.user.b + user;
+                float* bg = lane == 0 ? m.item.bg + pos_id : lane == 1 ? m.item.bg + neg_id : m.user.bg + user;
+                const float g0 = lane == 0 ? cs.pbg : lane == 1 ? nbg : cs.ubg;
+                const float g = lane == 0 ? -loss : loss;
+                red_add(b, -lr * rsqrt_ftz(g0) * g);
+                red_add(bg, g * g);
+            }
+        }
+        cur = nxt;
+        cs = ns;
+    }
+    cp_async_wait_all();
+    if (lane == 0) {
+        atomicAdd(&a.counters->positives, (unsigned long long)c_pos);
+        atomicAdd(&a.counters->negatives, (unsigned long long)c_neg);
+        atomicAdd(&a.counters->updates, (unsigned long long)c_upd);
+        atomicAdd(&a.counters->rejected, (unsigned long long)c_rej);
+    }
+}
+
+// ---- WARP, one SLOT per interaction (v4) -----------------------------------------
+// ncu on v2 (profiles/r1): once the dependent-load chain was pipelined the kernel became
+// issue-bound (66% issue-active, ~600 warp-instructions per interaction), because with one
+// warp per interaction every scalar step (Philox, membership search, control flow, the
+// user.positive dot) is executed by 32 lanes for ONE interaction.  v4 gives each interaction
+// the LPR = d/4 lanes that its rows need and runs NS = 32/LPR interactions per warp in
+// lockstep: the same instruction stream now serves NS interactions, no candidate row is ever
+// loaded speculatively, and the sampling rounds of the NS interactions overlap in time.
+// A slot that has found its negative (or exhausted max_sampled) idles until its warp-mates
+// finish; E[max of NS geometric draws] / NS < E[one draw] for the violation rates seen.
+//
+// Staging (cp.async.cg into double-buffered shared memory, issued one interaction ahead) and
+// the prefetched first membership probe are as in v2, per slot.
+template <int LPR>
+__device__ __forceinline__ bool slot_member(const int32_t* __restrict__ idx, int lo, int hi, int probe,
+                                            int key, bool need, int sub, unsigned slotmask) {
+    constexpr int LOG = LPR == 32 ? 5 : LPR == 16 ? 4 : LPR == 8 ? 3 : 2;
+    bool found = false, busy = need;
+    int len = hi - lo, v = probe;
+    while (__any_sync(LFM_FULL, busy)) {
+        const bool inr = busy && (len > LPR || sub < len);
+        const unsigned le = __ballot_sync(LFM_FULL, inr && v <= key) & slotmask;
+        const unsigned eq = __ballot_sync(LFM_FULL, inr && v == key) & slotmask;
+        if (busy) {
+            if (len <= LPR) {
+                found = eq != 0;
+                busy = false;
+            } else if (eq != 0) {
+                found = true;
+                busy = false;
+            } else {
+                const int c = __popc(le);  // pivots p_l = lo + (len*l >> LOG), p_0 = lo
+                if (c == 0) {
+                    busy = false;  // key < first element
+                } else {
+                    const int nlo = lo + (int)(((unsigned long long)(unsigned)len * (unsigned)(c - 1)) >> LOG);
+                    const int nhi = c == LPR ? hi : lo + (int)(((unsigned long long)(unsigned)len * (unsigned)c) >> LOG);
+                    lo = nlo + 1;
+                    hi = nhi;
+                    len = hi - lo;
+                    if (len <= 0) {
+                        busy = false;
+                    } else if (len <= LPR) {
+                        v = sub < len ? __ldg(idx + lo + sub) : -1;
+                    } else {
+                        v = __ldg(idx + lo + (int)(((unsigned long long)(unsigned)len * (unsigned)sub) >> LOG));
+                    }
+                }
+            }
+        }
+    }
+    return found;
+}
+template <int LPR>
+__device__ __forceinline__ int slot_probe_index(int lo, int hi, int sub) {
+    constexpr int LOG = LPR == 32 ? 5 : LPR == 16 ? 4 : LPR == 8 ? 3 : 2;
+    const int len = hi - lo;
+    if (len <= LPR) return sub < len ? lo + sub : -1;
+    return lo + (int)(((unsigned long long)(unsigned)len * (unsigned)sub) >> LOG);
+}
+
+template <int LPR, int MINB>
+__global__ void __launch_bounds__(256, MINB) fast_warp_v4_kernel(FitArgs a, const Tuple* __restrict__ tuples) {
+    constexpr int D = 4 * LPR;
+    constexpr int NS = 32 / LPR;
+    constexpr int BUFF = 4 * D;  // floats per slot per buffer: u, p, Gu, Gp rows
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int sub = lane % LPR, slot = lane / LPR;
+    const unsigned slotmask = (LPR == 32 ? 0xffffffffu : ((1u << LPR) - 1u)) << (slot * LPR);
+    float* sbuf = smem + ((size_t)wib * NS + slot) * 2 * BUFF;  // this slot's two buffers
+    const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+    const int n_tuples = (int)a.n;
+    const DevModel& m = a.model;
+    const float lr = m.lr;
+    const int n_items = a.itf.rows;
+    const int max_sampled = m.max_sampled;
+    unsigned c_pos = 0, c_neg = 0, c_upd = 0, c_rej = 0;  // per slot, kept on its sub == 0 lane
+
+    auto stage = [&](const Tuple& tp, float* buf, TupleScalars& sc) {
+        if (tp.user < 0) return;
+        cp_async16(buf + 0 * D + sub * 4, m.user.w + (size_t)tp.user * D + sub * 4);
+        cp_async16(buf + 1 * D + sub * 4, m.item.w + (size_t)tp.item * D + sub * 4);
+        cp_async16(buf + 2 * D + sub * 4, m.user.g + (size_t)tp.user * D + sub * 4);
+        cp_async16(buf + 3 * D + sub * 4, m.item.g + (size_t)tp.item * D + sub * 4);
+        sc.ub = __ldcg(m.user.b + tp.user);
+        sc.pb = __ldcg(m.item.b + tp.item);
+        sc.ubg = __ldcg(m.user.bg + tp.user);
+        sc.pbg = __ldcg(m.item.bg + tp.item);
+        sc.ps = __ldg(a.pos.indptr + tp.user);
+        sc.pe = __ldg(a.pos.indptr + tp.user + 1);
+        const int pi = slot_probe_index<LPR>(sc.ps, sc.pe, sub);
+        sc.probe = pi >= 0 ? __ldg(a.pos.indices + pi) : -1;
+    };
+    auto fetch = [&](int base) -> Tuple {
+        Tuple tp = {-1, 0, 0.0f, 0.0f};
+        const int t = base + slot;
+        if (base >= 0 && t < n_tuples) tp = tuples[t];
+        return tp;
+    };
+
+    int base = warp * NS;  // first tuple of this warp's group; groups are nwarps*NS apart
+    Tuple cur = fetch(base < n_tuples ? base : -1);
+    TupleScalars cs = {0.f, 0.f, 0.f, 0.f, 0, 0, -1};
+    stage(cur, sbuf, cs);
+    cp_async_commit();
+    int flip = 0;
+
+    for (; base < n_tuples; base += nwarps * NS, flip ^= 1) {
+        const int nbase = base + nwarps * NS;
+        Tuple nxt = fetch((nbase > 0 && nbase < n_tuples) ? nbase : -1);
+        TupleScalars ns = {0.f, 0.f, 0.f, 0.f, 0, 0, -1};
+        float* buf = sbuf + flip * BUFF;
+        float* nbuf = sbuf + (flip ^ 1) * BUFF;
+        cp_async_wait_all();
+        __syncwarp();
+        const bool valid = cur.user >= 0;
+        const int t = base + slot;
+        float4 u4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float pp = 0.0f;
+        if (valid) {
+            u4 = *(const float4*)(buf + 0 * D + sub * 4);
+            const float4 p4 = *(const float4*)(buf + 1 * D + sub * 4);
+            pp = dot4(u4, p4);
+        }
+        pp = slot_sum<LPR>(pp) + cs.ub + cs.pb;
+
+        // ---- rank sampling (T:855-899): every slot draws its own candidates in lockstep ----
+        int sampled = 0, neg_id = -1;
+        float loss = 0.0f;
+        float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        Philox4 r4 = {0u, 0u, 0u, 0u};
+        bool active = valid && max_sampled > 0;
+        for (int round = 0; __any_sync(LFM_FULL, active); round++) {
+            if ((round & 3) == 0)
+                r4 = philox7((uint32_t)t, 0u, (uint32_t)(round >> 2), 0u, a.seed, 0x4c464d31u);
+            const int w = round & 3;
+            const uint32_t r = w == 0 ? r4.x : w == 1 ? r4.y : w == 2 ? r4.z : r4.w;
+            const int cand = lfm_bounded(r, (uint32_t)n_items);
+            float qb = 0.0f;
+            if (active) {
+                q4 = ldcg4(m.item.w + (size_t)cand * D + sub * 4);
+                qb = __ldcg(m.item.b + cand);
+            }
+            const float np = slot_sum<LPR>(dot4(u4, q4)) + cs.ub + qb;
+            const bool viol = active && np > pp - 1.0f;
+            const bool member = slot_member<LPR>(a.pos.indices, cs.ps, cs.pe, cs.probe, cand, viol, sub, slotmask);
+            if (active) {
+                sampled++;
+                if (viol) {
+                    if (member) {
+                        if (sub == 0) c_rej++;
+                    } else {
+                        neg_id = cand;
+                        loss = fminf(cur.weight * (float)a.loss_table[sampled], (float)LFM_MAX_LOSS);
+                    }
+                }
+                active = neg_id < 0 && sampled < max_sampled;
+            }
+        }
+        if (valid && sub == 0) { c_pos++; c_neg += sampled; }
+
+        // ---- prefetch the next group while this one updates ----
+        stage(nxt, nbuf, ns);
+        cp_async_commit();
+
+        // ---- update (T:537-649): three rows + three biases per slot, one instruction stream ----
+        const bool upd = neg_id >= 0;
+        if (__any_sync(LFM_FULL, upd)) {
+            const size_t on = (size_t)(upd ? neg_id : 0) * D + sub * 4;
+            float4 gn = make_float4(1.f, 1.f, 1.f, 1.f);
+            float nbg = 1.0f;
+            if (upd) {
+                gn = ldcg4(m.item.g + on);            // the only fetch left on the critical path
+                if (sub == 1) nbg = __ldcg(m.item.bg + neg_id);
+            }
+            if (upd) {
+                const float4 p4 = *(const float4*)(buf + 1 * D + sub * 4);
+                const float4 gu = *(const float4*)(buf + 2 * D + sub * 4);
+                const float4 gp = *(const float4*)(buf + 3 * D + sub * 4);
+                const size_t op = (size_t)cur.item * D + sub * 4, ou = (size_t)cur.user * D + sub * 4;
+                const float lx = loss * u4.x, ly = loss * u4.y, lz = loss * u4.z, lw = loss * u4.w;
+                adagrad_row4_g(m.item.w + op, m.item.g + op, gp, lr, -lx, -ly, -lz, -lw);
+                adagrad_row4_g(m.user.w + ou, m.user.g + ou, gu, lr, loss * (q4.x - p4.x), loss * (q4.y - p4.y),
+                               loss * (q4.z - p4.z), loss * (q4.w - p4.w));
+                adagrad_row4_g(m.item.w + on, m.item.g + on, gn, lr, lx, ly, lz, lw);
+                if (sub < 3) {  // biases: sub 0 positive (-loss), 1 negative (+loss), 2 user (+loss)
+                    float* b = sub == 0 ? m.item.b + cur.item : sub == 1 ? m.item.b + neg_id : m.user.b + cur.user;
+                    float* bg = sub == 0 ? m.item.bg + cur.item : sub == 1 ? m.item.bg + neg_id : m.user.bg + cur.user;
+                    const float g0 = sub == 0 ? cs.pbg : sub == 1 ? nbg : cs.ubg;
+                    const float g = sub == 0 ? -loss : loss;
+                    red_add(b, -lr * rsqrt_ftz(g0) * g);
+                    red_add(bg, g * g);
+                }
+                if (sub == 0) c_upd++;
+            }
+        }
+        cur = nxt;
+        cs = ns;
+    }
+    cp_async_wait_all();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        c_pos += __shfl_xor_sync(LFM_FULL, c_pos, o);
+        c_neg += __shfl_xor_sync(LFM_FULL, c_neg, o);
+        c_upd += __shfl_xor_sync(LFM_FULL, c_upd, o);
+        c_rej += __shfl_xor_sync(LFM_FULL, c_rej, o);
+    }
+    if (lane == 0) {
+        atomicAdd(&a.counters->positives, (unsigned long long)c_pos);
+        atomicAdd(&a.counters->negatives, (unsigned long long)c_neg);
+        atomicAdd(&a.counters->updates, (unsigned long long)c_upd);
+        atomicAdd(&a.counters->rejected, (unsigned long long)c_rej);
+    }
+}
+
 // ---- logistic and BPR: one slot per interaction ------------------------------
 template <int LOSS, int LPR>
 __global__ void __launch_bounds__(256) fast_pair_kernel(FitArgs a, const Tuple* __restrict__ tuples) {
@@ -314,12 +799,68 @@ FastGrid fast_grid(K kernel, int64_t warps_wanted, int64_t warps_cap) {
     return g;
 }
 
+template <int LPR, int MINB>
+cudaError_t launch_warp_v2(const FitArgs& b, const Tuple* tp, int64_t count, cudaStream_t st) {
+    constexpr int D = 4 * LPR;
+    const size_t smem = (size_t)8 * 2 * 4 * D * sizeof(float);
+    auto kern = fast_warp_v2_kernel<LPR, MINB>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
+    if (per_sm < 1) per_sm = 1;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int64_t blocks = (int64_t)sms * per_sm;
+    int64_t need = (count + 7) / 8, cap = (lfm_inflight_cap(count) + 7) / 8;
+    if (blocks > need) blocks = need;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    kern<<<(int)blocks, 256, smem, st>>>(b, tp);
+    return cudaGetLastError();
+}
+
+template <int LPR, int MINB>
+cudaError_t launch_warp_v4(const FitArgs& b, const Tuple* tp, int64_t count, cudaStream_t st) {
+    constexpr int D = 4 * LPR;
+    constexpr int NS = 32 / LPR;
+    const size_t smem = (size_t)8 * NS * 2 * 4 * D * sizeof(float);
+    auto kern = fast_warp_v4_kernel<LPR, MINB>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
+    if (per_sm < 1) per_sm = 1;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int64_t groups = (count + NS - 1) / NS;
+    int64_t blocks = (int64_t)sms * per_sm;
+    int64_t need = (groups + 7) / 8, cap = ((lfm_inflight_cap(count) + NS - 1) / NS + 7) / 8;
+    if (blocks > need) blocks = need;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    kern<<<(int)blocks, 256, smem, st>>>(b, tp);
+    return cudaGetLastError();
+}
+
+// 0: v1 (warp per interaction); 1/2/3: v2 pipelined at 4/5/6 CTAs per SM;
+// 4/5/6: v4 (slot per interaction, pipelined) at 3/4/5 CTAs per SM
+static int g_tuning = 5;
+
 template <int LOSS, int LPR>
 cudaError_t launch_fast(const FitArgs& a, const Tuple* tuples, int64_t begin, int64_t count,
                         cudaStream_t st) {
     FitArgs b = a;
     b.n = count;
     const Tuple* tp = tuples + begin;
+    if constexpr (LOSS == LOSS_WARP) {
+        if (g_tuning == 1) return launch_warp_v2<LPR, 4>(b, tp, count, st);
+        if (g_tuning == 2) return launch_warp_v2<LPR, 5>(b, tp, count, st);
+        if (g_tuning == 3) return launch_warp_v2<LPR, 6>(b, tp, count, st);
+        if (g_tuning == 4) return launch_warp_v4<LPR, 3>(b, tp, count, st);
+        if (g_tuning == 5) return launch_warp_v4<LPR, 4>(b, tp, count, st);
+        if (g_tuning == 6) return launch_warp_v4<LPR, 5>(b, tp, count, st);
+    }
     if constexpr (LOSS == LOSS_WARP || LOSS == LOSS_KOS) {
         FastGrid g = fast_grid(fast_rank_kernel<LOSS, LPR>, count, lfm_inflight_cap(count));
         fast_rank_kernel<LOSS, LPR><<<g.blocks, g.threads, 0, st>>>(b, tp);
@@ -347,6 +888,12 @@ cudaError_t launch_fast_d(const FitArgs& a, const Tuple* tuples, int64_t begin, 
 
 }  // namespace
 
+extern "C" int lfm_set_tuning(int variant) {
+    int old = g_tuning;
+    if (variant >= 0 && variant <= 6) g_tuning = variant;
+    return old;
+}
+
 // Set by lfm_set_fast_path (tests use it to exercise the generic kernels on fast-eligible inputs).
 static int g_fast_enabled = 1;
 extern "C" int lfm_set_fast_path(int enabled) {
@@ -363,6 +910,7 @@ static cudaError_t lfm_try_launch_fast(int loss, const FitArgs& a, const Tuple* 
     if (!a.itf.identity || !a.usf.identity) return cudaSuccess;
     if (m.adadelta || a.item_alpha != 0.0 || a.user_alpha != 0.0) return cudaSuccess;
     if (loss == LOSS_KOS && a.nkos > 32) return cudaSuccess;
+    if (count > 0x7ff00000LL) return cudaSuccess;  // the fast kernels index tuples with int32
     // float4 path needs 16-byte aligned rows
     if ((((uintptr_t)m.item.w | (uintptr_t)m.item.g | (uintptr_t)m.user.w | (uintptr_t)m.user.g) & 15) != 0)
         return cudaSuccess;

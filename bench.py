@@ -378,7 +378,7 @@ def run_ours(args):
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                     "kernel": "fast_rank_kernel<WARP,16>", "kernel_ms": train_ms / args.steps,
+                     "kernel": fast.warp_kernel_name(D), "kernel_ms": train_ms / args.steps,
                      "algorithmic_bytes_per_step": abytes / args.steps},
         "cpu_baseline": cpu,
     }

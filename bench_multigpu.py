@@ -181,7 +181,7 @@ def run(args, rank, world, local):
                     "call": "per rank: lfm_plan_create(host pinned buffers) + epoch + all-reduce + lfm_plan_download"},
             "gpu_launches": int(sums[5].item()),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "kernel": "fast_rank_kernel<WARP,16>",
+                         "frac": achieved / peak, "traffic": None, "kernel": fast.warp_kernel_name(B.D),
                          "note": "per-GPU average"},
             "cpu_baseline": None,
         }))

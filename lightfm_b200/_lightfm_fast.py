@@ -90,6 +90,19 @@ def set_tuning(variant):
     return fn(int(variant))
 
 
+_TUNING_NAMES = {0: "fast_rank_kernel<WARP,LPR=d/4>", 1: "fast_warp_v2_kernel<LPR,4>",
+                 2: "fast_warp_v2_kernel<LPR,5>", 3: "fast_warp_v2_kernel<LPR,6>",
+                 4: "fast_warp_v4_kernel<d,1,3>", 5: "fast_warp_v4_kernel<d,1,4>",
+                 6: "fast_warp_v4_kernel<d,2,2>", 7: "fast_warp_v4_kernel<d,2,3>",
+                 8: "fast_warp_v4_kernel<d,2,4>"}
+
+
+def warp_kernel_name(d=64):
+    """Name of the WARP fast-path kernel the current tuning launches (for reports)."""
+    t = set_tuning(-1)  # out-of-range: returns the current value without changing it
+    return _TUNING_NAMES.get(t, "?").replace("<d,", "<%d," % d).replace("LPR", str(d // 4))
+
+
 def release_cache():
     _check(_lib.lfm_release_cache())
 

@@ -466,54 +466,84 @@ __global__ void __launch_bounds__(256, MINB) fast_warp_v2_kernel(FitArgs a, cons
     }
 }
 
-// ---- WARP, one SLOT per interaction (v4) -----------------------------------------
+// ---- WARP, one SLOT per interaction (v4/v5) --------------------------------------
 // ncu on v2 (profiles/r1): once the dependent-load chain was pipelined the kernel became
 // issue-bound (66% issue-active, ~600 warp-instructions per interaction), because with one
 // warp per interaction every scalar step (Philox, membership search, control flow, the
-// user.positive dot) is executed by 32 lanes for ONE interaction.  v4 gives each interaction
-// the LPR = d/4 lanes that its rows need and runs NS = 32/LPR interactions per warp in
-// lockstep: the same instruction stream now serves NS interactions, no candidate row is ever
-// loaded speculatively, and the sampling rounds of the NS interactions overlap in time.
-// A slot that has found its negative (or exhausted max_sampled) idles until its warp-mates
-// finish; E[max of NS geometric draws] / NS < E[one draw] for the violation rates seen.
+// user.positive dot) is executed by 32 lanes for ONE interaction.  Here each interaction gets
+// LPR = d / (4*VPL) lanes, each lane holding VPL float4 chunks of a row, and NS = 32/LPR
+// interactions run per warp in lockstep: one instruction stream serves NS interactions, no
+// candidate row is ever loaded speculatively, and the sampling rounds of the NS interactions
+// overlap in time.  A slot that has found its negative (or exhausted max_sampled) idles until
+// its warp-mates finish; E[max of NS geometric draws] / NS < E[one draw].
+//     d = 64 : VPL 1 -> 2 interactions / warp (v4) ; VPL 2 -> 4 interactions / warp (v5)
 //
-// Staging (cp.async.cg into double-buffered shared memory, issued one interaction ahead) and
-// the prefetched first membership probe are as in v2, per slot.
+// Staging (cp.async.cg into double-buffered shared memory, issued one group ahead) and the
+// prefetched first membership probe are as in v2, per slot.
+//
+// Membership of `key` in the sorted CSR row idx[lo, hi) by the LPR lanes of a slot.  Level 1
+// uses LPR probes that do not depend on the key and were prefetched with the row bounds
+// (len <= LPR: the row itself; else pivots lo + (len*l >> log2 LPR)).  Every further level is
+// 4*LPR-ary: each lane issues four independent probes, so a row of length L costs
+// ceil(log_{4 LPR}(L / LPR)) dependent L2 round trips instead of log2 L (T:270-284).
 template <int LPR>
 __device__ __forceinline__ bool slot_member(const int32_t* __restrict__ idx, int lo, int hi, int probe,
                                             int key, bool need, int sub, unsigned slotmask) {
     constexpr int LOG = LPR == 32 ? 5 : LPR == 16 ? 4 : LPR == 8 ? 3 : 2;
+    constexpr int W = 4 * LPR;  // fan-out of the deeper levels
     bool found = false, busy = need;
-    int len = hi - lo, v = probe;
-    while (__any_sync(LFM_FULL, busy)) {
+    if (!__any_sync(LFM_FULL, busy)) return false;
+    int len = hi - lo;
+    {   // level 1, from registers
         const bool inr = busy && (len > LPR || sub < len);
-        const unsigned le = __ballot_sync(LFM_FULL, inr && v <= key) & slotmask;
-        const unsigned eq = __ballot_sync(LFM_FULL, inr && v == key) & slotmask;
+        const unsigned le = __ballot_sync(LFM_FULL, inr && probe <= key) & slotmask;
+        const unsigned eq = __ballot_sync(LFM_FULL, inr && probe == key) & slotmask;
         if (busy) {
-            if (len <= LPR) {
-                found = eq != 0;
-                busy = false;
-            } else if (eq != 0) {
-                found = true;
-                busy = false;
-            } else {
-                const int c = __popc(le);  // pivots p_l = lo + (len*l >> LOG), p_0 = lo
-                if (c == 0) {
-                    busy = false;  // key < first element
-                } else {
-                    const int nlo = lo + (int)(((unsigned long long)(unsigned)len * (unsigned)(c - 1)) >> LOG);
-                    const int nhi = c == LPR ? hi : lo + (int)(((unsigned long long)(unsigned)len * (unsigned)c) >> LOG);
-                    lo = nlo + 1;
-                    hi = nhi;
-                    len = hi - lo;
-                    if (len <= 0) {
-                        busy = false;
-                    } else if (len <= LPR) {
-                        v = sub < len ? __ldg(idx + lo + sub) : -1;
-                    } else {
-                        v = __ldg(idx + lo + (int)(((unsigned long long)(unsigned)len * (unsigned)sub) >> LOG));
-                    }
-                }
+            const int c = __popc(le);
+            if (eq != 0) { found = true; busy = false; }
+            else if (len <= LPR || c == 0) { busy = false; }
+            else {
+                const int nlo = lo + (int)(((unsigned long long)(unsigned)len * (unsigned)(c - 1)) >> LOG);
+                const int nhi = c == LPR ? hi : lo + (int)(((unsigned long long)(unsigned)len * (unsigned)c) >> LOG);
+                lo = nlo + 1;
+                hi = nhi;
+                len = hi - lo;
+                if (len <= 0) busy = false;
+            }
+        }
+    }
+    while (__any_sync(LFM_FULL, busy)) {
+        // this lane's four probe positions: elements (len <= W) or pivots q_j = lo + (len*j / W)
+        int v[4];
+        bool in[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int j = sub * 4 + i;
+            const int pos = len <= W ? lo + j : lo + (int)(((unsigned long long)(unsigned)len * (unsigned)j) / W);
+            in[i] = busy && (len > W || j < len);
+            v[i] = in[i] ? __ldg(idx + pos) : 0;
+        }
+        int cnt = 0;
+        bool hit = false;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            cnt += (in[i] && v[i] <= key) ? 1 : 0;
+            hit |= in[i] && v[i] == key;
+        }
+        const bool anyhit = (__ballot_sync(LFM_FULL, hit) & slotmask) != 0;
+        int c = cnt;  // pivots are sorted, so the count of pivots <= key is the sum over lanes
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) c += __shfl_xor_sync(LFM_FULL, c, o);
+        if (busy) {
+            if (anyhit) { found = true; busy = false; }
+            else if (len <= W || c == 0) { busy = false; }
+            else {
+                const int nlo = lo + (int)(((unsigned long long)(unsigned)len * (unsigned)(c - 1)) / W);
+                const int nhi = c == W ? hi : lo + (int)(((unsigned long long)(unsigned)len * (unsigned)c) / W);
+                lo = nlo + 1;
+                hi = nhi;
+                len = hi - lo;
+                if (len <= 0) busy = false;
             }
         }
     }
@@ -527,9 +557,9 @@ __device__ __forceinline__ int slot_probe_index(int lo, int hi, int sub) {
     return lo + (int)(((unsigned long long)(unsigned)len * (unsigned)sub) >> LOG);
 }
 
-template <int LPR, int MINB>
+template <int D, int VPL, int MINB>
 __global__ void __launch_bounds__(256, MINB) fast_warp_v4_kernel(FitArgs a, const Tuple* __restrict__ tuples) {
-    constexpr int D = 4 * LPR;
+    constexpr int LPR = D / (4 * VPL);
     constexpr int NS = 32 / LPR;
     constexpr int BUFF = 4 * D;  // floats per slot per buffer: u, p, Gu, Gp rows
     extern __shared__ __align__(16) float smem[];
@@ -546,12 +576,18 @@ __global__ void __launch_bounds__(256, MINB) fast_warp_v4_kernel(FitArgs a, cons
     const int max_sampled = m.max_sampled;
     unsigned c_pos = 0, c_neg = 0, c_upd = 0, c_rej = 0;  // per slot, kept on its sub == 0 lane
 
+    // lane's chunk v of a row starts at float offset (sub + LPR*v)*4: consecutive lanes read
+    // consecutive 16 B, so every load instruction of a slot is one contiguous LPR*16 B piece
     auto stage = [&](const Tuple& tp, float* buf, TupleScalars& sc) {
         if (tp.user < 0) return;
-        cp_async16(buf + 0 * D + sub * 4, m.user.w + (size_t)tp.user * D + sub * 4);
-        cp_async16(buf + 1 * D + sub * 4, m.item.w + (size_t)tp.item * D + sub * 4);
-        cp_async16(buf + 2 * D + sub * 4, m.user.g + (size_t)tp.user * D + sub * 4);
-        cp_async16(buf + 3 * D + sub * 4, m.item.g + (size_t)tp.item * D + sub * 4);
+#pragma unroll
+        for (int v = 0; v < VPL; v++) {
+            const int o = (sub + LPR * v) * 4;
+            cp_async16(buf + 0 * D + o, m.user.w + (size_t)tp.user * D + o);
+            cp_async16(buf + 1 * D + o, m.item.w + (size_t)tp.item * D + o);
+            cp_async16(buf + 2 * D + o, m.user.g + (size_t)tp.user * D + o);
+            cp_async16(buf + 3 * D + o, m.item.g + (size_t)tp.item * D + o);
+        }
         sc.ub = __ldcg(m.user.b + tp.user);
         sc.pb = __ldcg(m.item.b + tp.item);
         sc.ubg = __ldcg(m.user.bg + tp.user);
@@ -585,19 +621,24 @@ __global__ void __launch_bounds__(256, MINB) fast_warp_v4_kernel(FitArgs a, cons
         __syncwarp();
         const bool valid = cur.user >= 0;
         const int t = base + slot;
-        float4 u4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 u[VPL];
         float pp = 0.0f;
-        if (valid) {
-            u4 = *(const float4*)(buf + 0 * D + sub * 4);
-            const float4 p4 = *(const float4*)(buf + 1 * D + sub * 4);
-            pp = dot4(u4, p4);
+#pragma unroll
+        for (int v = 0; v < VPL; v++) {
+            u[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) {
+                u[v] = *(const float4*)(buf + 0 * D + (sub + LPR * v) * 4);
+                pp += dot4(u[v], *(const float4*)(buf + 1 * D + (sub + LPR * v) * 4));
+            }
         }
         pp = slot_sum<LPR>(pp) + cs.ub + cs.pb;
 
         // ---- rank sampling (T:855-899): every slot draws its own candidates in lockstep ----
         int sampled = 0, neg_id = -1;
         float loss = 0.0f;
-        float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 q[VPL];
+#pragma unroll
+        for (int v = 0; v < VPL; v++) q[v] = make_float4(0.f, 0.f, 0.f, 0.f);
         Philox4 r4 = {0u, 0u, 0u, 0u};
         bool active = valid && max_sampled > 0;
         for (int round = 0; __any_sync(LFM_FULL, active); round++) {
@@ -608,10 +649,14 @@ __global__ void __launch_bounds__(256, MINB) fast_warp_v4_kernel(FitArgs a, cons
             const int cand = lfm_bounded(r, (uint32_t)n_items);
             float qb = 0.0f;
             if (active) {
-                q4 = ldcg4(m.item.w + (size_t)cand * D + sub * 4);
+#pragma unroll
+                for (int v = 0; v < VPL; v++) q[v] = ldcg4(m.item.w + (size_t)cand * D + (sub + LPR * v) * 4);
                 qb = __ldcg(m.item.b + cand);
             }
-            const float np = slot_sum<LPR>(dot4(u4, q4)) + cs.ub + qb;
+            float part = 0.0f;
+#pragma unroll
+            for (int v = 0; v < VPL; v++) part += dot4(u[v], q[v]);
+            const float np = slot_sum<LPR>(part) + cs.ub + qb;
             const bool viol = active && np > pp - 1.0f;
             const bool member = slot_member<LPR>(a.pos.indices, cs.ps, cs.pe, cs.probe, cand, viol, sub, slotmask);
             if (active) {
@@ -636,23 +681,28 @@ __global__ void __launch_bounds__(256, MINB) fast_warp_v4_kernel(FitArgs a, cons
         // ---- update (T:537-649): three rows + three biases per slot, one instruction stream ----
         const bool upd = neg_id >= 0;
         if (__any_sync(LFM_FULL, upd)) {
-            const size_t on = (size_t)(upd ? neg_id : 0) * D + sub * 4;
-            float4 gn = make_float4(1.f, 1.f, 1.f, 1.f);
+            const size_t on = (size_t)(upd ? neg_id : 0) * D;
+            float4 gn[VPL];
             float nbg = 1.0f;
-            if (upd) {
-                gn = ldcg4(m.item.g + on);            // the only fetch left on the critical path
+            if (upd) {  // the only fetches left on the critical path
+#pragma unroll
+                for (int v = 0; v < VPL; v++) gn[v] = ldcg4(m.item.g + on + (sub + LPR * v) * 4);
                 if (sub == 1) nbg = __ldcg(m.item.bg + neg_id);
             }
             if (upd) {
-                const float4 p4 = *(const float4*)(buf + 1 * D + sub * 4);
-                const float4 gu = *(const float4*)(buf + 2 * D + sub * 4);
-                const float4 gp = *(const float4*)(buf + 3 * D + sub * 4);
-                const size_t op = (size_t)cur.item * D + sub * 4, ou = (size_t)cur.user * D + sub * 4;
-                const float lx = loss * u4.x, ly = loss * u4.y, lz = loss * u4.z, lw = loss * u4.w;
-                adagrad_row4_g(m.item.w + op, m.item.g + op, gp, lr, -lx, -ly, -lz, -lw);
-                adagrad_row4_g(m.user.w + ou, m.user.g + ou, gu, lr, loss * (q4.x - p4.x), loss * (q4.y - p4.y),
-                               loss * (q4.z - p4.z), loss * (q4.w - p4.w));
-                adagrad_row4_g(m.item.w + on, m.item.g + on, gn, lr, lx, ly, lz, lw);
+                const size_t op = (size_t)cur.item * D, ou = (size_t)cur.user * D;
+#pragma unroll
+                for (int v = 0; v < VPL; v++) {
+                    const int o = (sub + LPR * v) * 4;
+                    const float4 p4 = *(const float4*)(buf + 1 * D + o);
+                    const float4 gu = *(const float4*)(buf + 2 * D + o);
+                    const float4 gp = *(const float4*)(buf + 3 * D + o);
+                    const float lx = loss * u[v].x, ly = loss * u[v].y, lz = loss * u[v].z, lw = loss * u[v].w;
+                    adagrad_row4_g(m.item.w + op + o, m.item.g + op + o, gp, lr, -lx, -ly, -lz, -lw);
+                    adagrad_row4_g(m.user.w + ou + o, m.user.g + ou + o, gu, lr, loss * (q[v].x - p4.x),
+                                   loss * (q[v].y - p4.y), loss * (q[v].z - p4.z), loss * (q[v].w - p4.w));
+                    adagrad_row4_g(m.item.w + on + o, m.item.g + on + o, gn[v], lr, lx, ly, lz, lw);
+                }
                 if (sub < 3) {  // biases: sub 0 positive (-loss), 1 negative (+loss), 2 user (+loss)
                     float* b = sub == 0 ? m.item.b + cur.item : sub == 1 ? m.item.b + neg_id : m.user.b + cur.user;
                     float* bg = sub == 0 ? m.item.bg + cur.item : sub == 1 ? m.item.bg + neg_id : m.user.bg + cur.user;
@@ -820,12 +870,12 @@ cudaError_t launch_warp_v2(const FitArgs& b, const Tuple* tp, int64_t count, cud
     return cudaGetLastError();
 }
 
-template <int LPR, int MINB>
+template <int D, int VPL, int MINB>
 cudaError_t launch_warp_v4(const FitArgs& b, const Tuple* tp, int64_t count, cudaStream_t st) {
-    constexpr int D = 4 * LPR;
+    constexpr int LPR = D / (4 * VPL);
     constexpr int NS = 32 / LPR;
     const size_t smem = (size_t)8 * NS * 2 * 4 * D * sizeof(float);
-    auto kern = fast_warp_v4_kernel<LPR, MINB>;
+    auto kern = fast_warp_v4_kernel<D, VPL, MINB>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
@@ -844,8 +894,9 @@ cudaError_t launch_warp_v4(const FitArgs& b, const Tuple* tp, int64_t count, cud
 }
 
 // 0: v1 (warp per interaction); 1/2/3: v2 pipelined at 4/5/6 CTAs per SM;
-// 4/5/6: v4 (slot per interaction, pipelined) at 3/4/5 CTAs per SM
-static int g_tuning = 5;
+// 4/5: v4 (slot per interaction, 1 chunk per lane) at 3/4 CTAs per SM;
+// 6/7/8: v5 (2 chunks per lane, twice the interactions per warp; d >= 32) at 2/3/4 CTAs per SM
+static int g_tuning = 7;
 
 template <int LOSS, int LPR>
 cudaError_t launch_fast(const FitArgs& a, const Tuple* tuples, int64_t begin, int64_t count,
@@ -857,9 +908,16 @@ cudaError_t launch_fast(const FitArgs& a, const Tuple* tuples, int64_t begin, in
         if (g_tuning == 1) return launch_warp_v2<LPR, 4>(b, tp, count, st);
         if (g_tuning == 2) return launch_warp_v2<LPR, 5>(b, tp, count, st);
         if (g_tuning == 3) return launch_warp_v2<LPR, 6>(b, tp, count, st);
-        if (g_tuning == 4) return launch_warp_v4<LPR, 3>(b, tp, count, st);
-        if (g_tuning == 5) return launch_warp_v4<LPR, 4>(b, tp, count, st);
-        if (g_tuning == 6) return launch_warp_v4<LPR, 5>(b, tp, count, st);
+        constexpr int DD = 4 * LPR;
+        if (g_tuning == 4) return launch_warp_v4<DD, 1, 3>(b, tp, count, st);
+        if (g_tuning == 5) return launch_warp_v4<DD, 1, 4>(b, tp, count, st);
+        if constexpr (DD >= 32) {
+            if (g_tuning == 6) return launch_warp_v4<DD, 2, 2>(b, tp, count, st);
+            if (g_tuning == 7) return launch_warp_v4<DD, 2, 3>(b, tp, count, st);
+            if (g_tuning == 8) return launch_warp_v4<DD, 2, 4>(b, tp, count, st);
+        } else if (g_tuning >= 6) {
+            return launch_warp_v4<DD, 1, 4>(b, tp, count, st);
+        }
     }
     if constexpr (LOSS == LOSS_WARP || LOSS == LOSS_KOS) {
         FastGrid g = fast_grid(fast_rank_kernel<LOSS, LPR>, count, lfm_inflight_cap(count));
@@ -890,7 +948,7 @@ cudaError_t launch_fast_d(const FitArgs& a, const Tuple* tuples, int64_t begin, 
 
 extern "C" int lfm_set_tuning(int variant) {
     int old = g_tuning;
-    if (variant >= 0 && variant <= 6) g_tuning = variant;
+    if (variant >= 0 && variant <= 8) g_tuning = variant;
     return old;
 }
 

@@ -222,13 +222,19 @@ def reference_epoch(fast, prob, sample, threads, rs):
 
 
 def calibrate_reference(fast, prob, threads, target_s):
+    """Pick the thread count the reference runs fastest with on this host (its OpenMP loop does
+    not always scale to every hardware thread), then size the per-step sample for ~target_s."""
     rs = np.random.RandomState(0)
-    probe = min(prob.nnz, 400_000)
+    probe = min(prob.nnz, 300_000)
     reference_epoch(fast, prob, min(prob.nnz, 100_000), threads, rs)  # warm caches / page in
-    dt = reference_epoch(fast, prob, probe, threads, rs)
-    rate = probe / dt
-    sample = int(min(prob.nnz, max(probe, rate * target_s)))
-    return sample, rate
+    cands = sorted({t for t in (threads, threads // 2, threads // 4, 32, 16, 8) if 1 <= t <= threads})
+    best_t, best_rate = threads, 0.0
+    for t in cands:
+        rate = probe / reference_epoch(fast, prob, probe, t, rs)
+        if rate > best_rate:
+            best_t, best_rate = t, rate
+    sample = int(min(prob.nnz, max(probe, best_rate * target_s)))
+    return sample, best_rate, best_t
 
 
 def run_reference_arm(args):
@@ -245,14 +251,15 @@ def run_reference_arm(args):
     device = "cuda" if torch.cuda.is_available() else "cpu"
     prob = Problem(N_USERS, N_ITEMS, args.nnz, D, seed=2, device=device, pin=False)
     budget = 150.0 / max(1, args.steps + args.warmup)
-    sample, _ = calibrate_reference(fast, prob, threads, target_s=min(8.0, max(1.0, budget)))
+    sample, _, threads = calibrate_reference(fast, prob, threads, target_s=min(8.0, max(1.0, budget)))
     rs = np.random.RandomState(1)
     for _ in range(args.warmup):
         reference_epoch(fast, prob, sample, threads, rs)
     times = [reference_epoch(fast, prob, sample, threads, rs) for _ in range(args.steps)]
     total = sum(times)
     value = sample * args.steps / total
-    desc = "first %d of the %d shuffled interactions per step, full 138493x26744 tables" % (sample, prob.nnz)
+    desc = ("first %d of the %d shuffled interactions per step, full 138493x26744 tables, %d OpenMP threads "
+            "(fastest of the counts probed on this %d-thread host)" % (sample, prob.nnz, threads, os.cpu_count() or 1))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
@@ -323,6 +330,13 @@ def run_ours(args):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    # dram__bytes_read.sum + dram__bytes_write.sum of one SGD-kernel launch, from the committed
+    # `ncu --set full` capture of this same command (profiles/README.md)
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(fast.warp_kernel_name(D))
+    except Exception:
+        pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback"
 
@@ -351,11 +365,12 @@ def run_ours(args):
             ref_fast, kind = load_reference_native()
             cores = os.cpu_count() or 1
             cpu_prob = prob
-            sample, _ = calibrate_reference(ref_fast, cpu_prob, cores, target_s=12.0)
+            sample, _, cores = calibrate_reference(ref_fast, cpu_prob, cores, target_s=12.0)
             dt = reference_epoch(ref_fast, cpu_prob, sample, cores, np.random.RandomState(3))
             cpu = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "reference",
                    "sample": "one fit_warp call on the first %d of %d shuffled interactions, %d OpenMP "
-                             "threads, build=%s" % (sample, prob.nnz, cores, kind)}
+                             "threads (fastest of the counts probed on this %d-thread host), build=%s"
+                             % (sample, prob.nnz, cores, os.cpu_count() or 1, kind)}
         except Exception as exc:  # pragma: no cover
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
                    "sample": "unavailable: %s" % exc}
@@ -377,7 +392,7 @@ def run_ours(args):
                 "call": "lightfm_b200._lightfm_fast.fit_warp(host pinned buffers)"},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "kernel": fast.warp_kernel_name(D), "kernel_ms": train_ms / args.steps,
                      "algorithmic_bytes_per_step": abytes / args.steps},
         "cpu_baseline": cpu,

@@ -83,16 +83,15 @@ def set_inflight_divisor(divisor):
 
 
 def set_tuning(variant):
-    """WARP fast-path kernel variant: 0 = v1, 1/2/3 = pipelined v2 at 4/5/6 CTAs per SM."""
+    """WARP fast-path kernel variant: 0 = warp per interaction (v1); 4/5 = slot per interaction,
+    one float4 per lane, 3/4 CTAs per SM; 6/7/8 = two float4 per lane, 2/3/4 CTAs per SM."""
     fn = _lib.lfm_set_tuning
     fn.restype = ctypes.c_int
     fn.argtypes = [ctypes.c_int]
     return fn(int(variant))
 
 
-_TUNING_NAMES = {0: "fast_rank_kernel<WARP,LPR=d/4>", 1: "fast_warp_v2_kernel<LPR,4>",
-                 2: "fast_warp_v2_kernel<LPR,5>", 3: "fast_warp_v2_kernel<LPR,6>",
-                 4: "fast_warp_v4_kernel<d,1,3>", 5: "fast_warp_v4_kernel<d,1,4>",
+_TUNING_NAMES = {0: "fast_rank_kernel<WARP,LPR=d/4>", 4: "fast_warp_v4_kernel<d,1,3>", 5: "fast_warp_v4_kernel<d,1,4>",
                  6: "fast_warp_v4_kernel<d,2,2>", 7: "fast_warp_v4_kernel<d,2,3>",
                  8: "fast_warp_v4_kernel<d,2,4>"}
 

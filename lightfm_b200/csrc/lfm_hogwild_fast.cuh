@@ -205,18 +205,7 @@ __global__ void __launch_bounds__(256) fast_rank_kernel(FitArgs a, const Tuple* 
     }
 }
 
-// ---- WARP, software-pipelined (v2) ---------------------------------------------
-// Same algorithm as fast_rank_kernel<LOSS_WARP>, restructured to shorten the per-interaction
-// chain of dependent L2 round trips (ncu r1: long-scoreboard stalls dominate, DRAM at 9%):
-//   * while interaction i is in its sampling loop, the tuple of interaction i+1 is loaded;
-//   * before interaction i's update, cp.async (LDGSTS, .cg = L2-coherent) stages interaction
-//     i+1's user row, positive row and their two accumulator rows into shared memory
-//     (double-buffered, 4 rows x d floats per buffer per warp) and its scalars (biases, CSR
-//     row bounds) into registers, so they arrive during the update / loop turn-around;
-//   * the accumulator rows of user and positive are thereby already on chip at update time;
-//     only the sampled negative's accumulator row is fetched on the critical path.
-// Philox4x32-7 (BigCrush-clean per Salmon et al.) with all four outputs consumed;
-// rsqrt.approx.ftz (G >= 1 under adagrad, no denormals); 32-bit per-warp counters.
+// ---- staging helpers (cp.async = LDGSTS, .cg: L2-coherent, bypasses L1) ---------
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
@@ -248,226 +237,13 @@ __device__ __forceinline__ void adagrad_row4_g(float* w, float* G, const float4&
 
 struct TupleScalars {
     float ub, pb;    // user / positive-item bias
-    float ubg, pbg;  // their Adagrad accumulators (consumed by lanes 2 / 0 at update time)
     int ps, pe;      // bounds of the user's row in the positives CSR
-    int probe;       // lane's first-level probe of that row (key independent, see warp_member2)
+    int probe;       // lane's first-level probe of that row (key independent, see slot_member)
 };
 
-// Membership of `key` in the sorted row idx[lo, hi) with the first level already in registers.
-// Level 1 (prefetched by the caller, independent of the key):
-//     len <= 32 : probe = idx[lo + lane]                     (the whole row)
-//     len  > 32 : probe = idx[lo + (len * lane >> 5)]        (32 pivots, pivot 0 = first element)
-// so a violating negative costs zero (short rows) or one dependent L2 round trip per further
-// factor 32 of row length, instead of log2(len) as in the reference's bsearch (T:270-284).
-__device__ __forceinline__ int probe_index(int lo, int hi, int lane) {
-    const int len = hi - lo;
-    if (len <= 32) return lane < len ? lo + lane : -1;
-    return lo + (int)(((unsigned long long)(unsigned)len * (unsigned)lane) >> 5);
-}
-__device__ __forceinline__ bool warp_member2(const int32_t* __restrict__ idx, int lo, int hi, int probe,
-                                             int key, int lane) {
-    int len = hi - lo;
-    if (len <= 32) return __any_sync(LFM_FULL, lane < len && probe == key);
-    int v = probe;
-    while (true) {
-        // pivots p_l = lo + (len*l >> 5), l = 0..31, p_0 = lo; c = number of pivots <= key
-        const unsigned le = __ballot_sync(LFM_FULL, v <= key);
-        const int c = __popc(le);
-        if (c == 0) return false;  // key < first element
-        if (__any_sync(LFM_FULL, v == key)) return true;
-        const int nlo = lo + (int)(((unsigned long long)(unsigned)len * (unsigned)(c - 1)) >> 5);
-        const int nhi = c == 32 ? hi : lo + (int)(((unsigned long long)(unsigned)len * (unsigned)c) >> 5);
-        lo = nlo + 1;  // idx[nlo] != key (checked above)
-        hi = nhi;
-        len = hi - lo;
-        if (len <= 0) return false;
-        if (len <= 32) {
-            v = lane < len ? __ldg(idx + lo + lane) : -1;
-            return __any_sync(LFM_FULL, lane < len && v == key);
-        }
-        v = __ldg(idx + lo + (int)(((unsigned long long)(unsigned)len * (unsigned)lane) >> 5));
-    }
-}
-
-template <int LPR, int MINB>
-__global__ void __launch_bounds__(256, MINB) fast_warp_v2_kernel(FitArgs a, const Tuple* __restrict__ tuples) {
-    constexpr int D = 4 * LPR;
-    constexpr int NS = 32 / LPR;
-    constexpr int ROWF = D;               // floats per staged row
-    constexpr int BUFF = 4 * ROWF;        // u, p, Gu, Gp
-    extern __shared__ __align__(16) float smem[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int sub = lane % LPR, slot = lane / LPR;
-    float* wbuf = smem + (size_t)wib * 2 * BUFF;
-    const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
-    const int n_tuples = (int)a.n;  // no_examples < 2^31 (checked by the host layer)
-    const DevModel& m = a.model;
-    const float lr = m.lr;
-    const int n_items = a.itf.rows;
-    const int max_sampled = m.max_sampled;
-    unsigned c_pos = 0, c_neg = 0, c_upd = 0, c_rej = 0;
-
-    // stage the four rows of one interaction: 4*LPR chunks of 16 B spread over the 32 lanes
-    auto stage = [&](const Tuple& tp, float* buf, TupleScalars& sc) {
-        if (tp.user < 0) return;
-#pragma unroll
-        for (int c = lane; c < 4 * LPR; c += 32) {
-            const int row = c / LPR, ch = c % LPR;  // row: 0 user w, 1 item w, 2 user g, 3 item g
-            const float* base = (row & 2) ? ((row & 1) ? m.item.g : m.user.g)
-                                          : ((row & 1) ? m.item.w : m.user.w);
-            const int id = (row & 1) ? tp.item : tp.user;
-            cp_async16(buf + row * ROWF + ch * 4, base + (size_t)id * D + ch * 4);
-        }
-        sc.ub = __ldcg(m.user.b + tp.user);
-        sc.pb = __ldcg(m.item.b + tp.item);
-        sc.ubg = __ldcg(m.user.bg + tp.user);
-        sc.pbg = __ldcg(m.item.bg + tp.item);
-        sc.ps = __ldg(a.pos.indptr + tp.user);
-        sc.pe = __ldg(a.pos.indptr + tp.user + 1);
-        const int pi = probe_index(sc.ps, sc.pe, lane);
-        sc.probe = pi >= 0 ? __ldg(a.pos.indices + pi) : -1;
-    };
-
-    int t = warp;
-    Tuple cur = {-1, 0, 0.0f, 0.0f};
-    TupleScalars cs = {0.f, 0.f, 0.f, 0.f, 0, 0, -1};
-    if (t < n_tuples) cur = tuples[t];
-    stage(cur, wbuf, cs);
-    cp_async_commit();
-    int flip = 0;
-
-    for (; t < n_tuples; t += nwarps, flip ^= 1) {
-        Tuple nxt = {-1, 0, 0.0f, 0.0f};
-        TupleScalars ns = {0.f, 0.f, 0.f, 0.f, 0, 0, -1};
-        if (t + nwarps < n_tuples && t + nwarps > 0) nxt = tuples[t + nwarps];
-        float* buf = wbuf + flip * BUFF;
-        float* nbuf = wbuf + (flip ^ 1) * BUFF;
-        cp_async_wait_all();
-        __syncwarp();
-        if (cur.user < 0) {
-            stage(nxt, nbuf, ns);
-            cp_async_commit();
-            cur = nxt;
-            cs = ns;
-            continue;
-        }
-        c_pos++;
-        const int user = cur.user, pos_id = cur.item;
-        const float4 u4 = *(const float4*)(buf + 0 * ROWF + sub * 4);
-        float pp;
-        {
-            const float4 p4 = *(const float4*)(buf + 1 * ROWF + sub * 4);
-            pp = slot_sum<LPR>(dot4(u4, p4)) + cs.ub + cs.pb;
-        }
-        // ---- rank sampling, NS speculative candidates per round ----
-        int sampled = 0, neg_id = -1, neg_lane = 0;
-        float loss = 0.0f;
-        float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        uint32_t ctr = 0;
-        Philox4 r4 = {0u, 0u, 0u, 0u};
-        int have = 0;  // unread 32-bit outputs left in r4 (per slot stream: slot-th lane group)
-        while (sampled < max_sampled && neg_id < 0) {
-            const int nb = min(NS, max_sampled - sampled);
-            // one Philox call yields 4 words; each round consumes NS words (one per slot)
-            uint32_t r;
-            if (NS >= 4) {
-                r4 = philox7((uint32_t)t, 0u, ctr + (slot >> 2), 0u, a.seed, 0x4c464d31u);
-                ctr += NS / 4;
-                r = (slot & 3) == 0 ? r4.x : (slot & 3) == 1 ? r4.y : (slot & 3) == 2 ? r4.z : r4.w;
-            } else {
-                if (have < NS) {
-                    r4 = philox7((uint32_t)t, 0u, ctr++, 0u, a.seed, 0x4c464d31u);
-                    have = 4;
-                }
-                const int idx = (4 - have) + slot;  // NS in {1,2}: words are handed out in order
-                r = idx == 0 ? r4.x : idx == 1 ? r4.y : idx == 2 ? r4.z : r4.w;
-                have -= NS;
-            }
-            const int cand = lfm_bounded(r, (uint32_t)n_items);
-            const bool act = slot < nb;
-            if (act) q4 = ldcg4(m.item.w + (size_t)cand * D + sub * 4);
-            const float qb = act ? __ldcg(m.item.b + cand) : 0.0f;
-            const float np = slot_sum<LPR>(dot4(u4, q4)) + cs.ub + qb;
-            unsigned vm = __ballot_sync(LFM_FULL, act && sub == 0 && np > pp - 1.0f);
-            int consumed = nb;
-            while (vm) {
-                const int first = __ffs(vm) - 1;
-                const int ck = __shfl_sync(LFM_FULL, cand, first);
-                if (warp_member2(a.pos.indices, cs.ps, cs.pe, cs.probe, ck, lane)) {
-                    c_rej++;
-                    vm &= vm - 1;
-                    continue;
-                }
-                const int k = first / LPR;
-                consumed = k + 1;
-                neg_id = ck;
-                neg_lane = first;
-                loss = fminf(cur.weight * (float)a.loss_table[sampled + k + 1], (float)LFM_MAX_LOSS);
-                break;
-            }
-            sampled += consumed;
-            c_neg += consumed;
-        }
-        // ---- prefetch the next interaction while this one updates ----
-        stage(nxt, nbuf, ns);
-        cp_async_commit();
-
-        if (neg_id >= 0) {
-            c_upd++;
-            // the only fetches left on the critical path: the negative's accumulator row and
-            // its bias accumulator -- issued together, before any arithmetic
-            const size_t on = (size_t)neg_id * D + sub * 4;
-            float4 gn = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (NS == 1 || slot == 1 % NS) gn = ldcg4(m.item.g + on);
-            float nbg = 1.0f;
-            if (lane == 1) nbg = __ldcg(m.item.bg + neg_id);
-            float4 n4;
-            n4.x = __shfl_sync(LFM_FULL, q4.x, neg_lane + sub);
-            n4.y = __shfl_sync(LFM_FULL, q4.y, neg_lane + sub);
-            n4.z = __shfl_sync(LFM_FULL, q4.z, neg_lane + sub);
-            n4.w = __shfl_sync(LFM_FULL, q4.w, neg_lane + sub);
-#pragma unroll
-            for (int task = slot; task < 3; task += NS) {
-                if (task == 0) {  // positive item row: gradient -loss * u ; G row already staged
-                    const float4 g0 = *(const float4*)(buf + 3 * ROWF + sub * 4);
-                    size_t o = (size_t)pos_id * D + sub * 4;
-                    adagrad_row4_g(m.item.w + o, m.item.g + o, g0, lr, -loss * u4.x, -loss * u4.y,
-                                   -loss * u4.z, -loss * u4.w);
-                } else if (task == 1) {  // negative item row: +loss * u
-                    adagrad_row4_g(m.item.w + on, m.item.g + on, gn, lr, loss * u4.x, loss * u4.y,
-                                   loss * u4.z, loss * u4.w);
-                } else {  // user row: loss * (neg - pos)
-                    const float4 g0 = *(const float4*)(buf + 2 * ROWF + sub * 4);
-                    const float4 p4 = *(const float4*)(buf + 1 * ROWF + sub * 4);
-                    size_t o = (size_t)user * D + sub * 4;
-                    adagrad_row4_g(m.user.w + o, m.user.g + o, g0, lr, loss * (n4.x - p4.x),
-                                   loss * (n4.y - p4.y), loss * (n4.z - p4.z), loss * (n4.w - p4.w));
-                }
-            }
-            if (lane < 3) {  // biases: lane 0 positive (-loss), lane 1 negative (+loss), lane 2 user (+loss)
-                float* b = lane == 0 ? m.item.b + pos_id : lane == 1 ? m.item.b + neg_id : m.user.b + user;
-                float* bg = lane == 0 ? m.item.bg + pos_id : lane == 1 ? m.item.bg + neg_id : m.user.bg + user;
-                const float g0 = lane == 0 ? cs.pbg : lane == 1 ? nbg : cs.ubg;
-                const float g = lane == 0 ? -loss : loss;
-                red_add(b, -lr * rsqrt_ftz(g0) * g);
-                red_add(bg, g * g);
-            }
-        }
-        cur = nxt;
-        cs = ns;
-    }
-    cp_async_wait_all();
-    if (lane == 0) {
-        atomicAdd(&a.counters->positives, (unsigned long long)c_pos);
-        atomicAdd(&a.counters->negatives, (unsigned long long)c_neg);
-        atomicAdd(&a.counters->updates, (unsigned long long)c_upd);
-        atomicAdd(&a.counters->rejected, (unsigned long long)c_rej);
-    }
-}
-
 // ---- WARP, one SLOT per interaction (v4/v5) --------------------------------------
-// ncu on v2 (profiles/r1): once the dependent-load chain was pipelined the kernel became
+// ncu (profiles/r1_ncu_v3_summary.txt): once the dependent-load chain of the warp-per-interaction
+// kernel was pipelined it became
 // issue-bound (66% issue-active, ~600 warp-instructions per interaction), because with one
 // warp per interaction every scalar step (Philox, membership search, control flow, the
 // user.positive dot) is executed by 32 lanes for ONE interaction.  Here each interaction gets
@@ -479,7 +255,7 @@ __global__ void __launch_bounds__(256, MINB) fast_warp_v2_kernel(FitArgs a, cons
 //     d = 64 : VPL 1 -> 2 interactions / warp (v4) ; VPL 2 -> 4 interactions / warp (v5)
 //
 // Staging (cp.async.cg into double-buffered shared memory, issued one group ahead) and the
-// prefetched first membership probe are as in v2, per slot.
+// prefetched first membership probe are per slot.
 //
 // Membership of `key` in the sorted CSR row idx[lo, hi) by the LPR lanes of a slot.  Level 1
 // uses LPR probes that do not depend on the key and were prefetched with the row bounds
@@ -590,8 +366,6 @@ __global__ void __launch_bounds__(256, MINB) fast_warp_v4_kernel(FitArgs a, cons
         }
         sc.ub = __ldcg(m.user.b + tp.user);
         sc.pb = __ldcg(m.item.b + tp.item);
-        sc.ubg = __ldcg(m.user.bg + tp.user);
-        sc.pbg = __ldcg(m.item.bg + tp.item);
         sc.ps = __ldg(a.pos.indptr + tp.user);
         sc.pe = __ldg(a.pos.indptr + tp.user + 1);
         const int pi = slot_probe_index<LPR>(sc.ps, sc.pe, sub);
@@ -606,7 +380,7 @@ __global__ void __launch_bounds__(256, MINB) fast_warp_v4_kernel(FitArgs a, cons
 
     int base = warp * NS;  // first tuple of this warp's group; groups are nwarps*NS apart
     Tuple cur = fetch(base < n_tuples ? base : -1);
-    TupleScalars cs = {0.f, 0.f, 0.f, 0.f, 0, 0, -1};
+    TupleScalars cs = {0.f, 0.f, 0, 0, -1};
     stage(cur, sbuf, cs);
     cp_async_commit();
     int flip = 0;
@@ -614,7 +388,7 @@ __global__ void __launch_bounds__(256, MINB) fast_warp_v4_kernel(FitArgs a, cons
     for (; base < n_tuples; base += nwarps * NS, flip ^= 1) {
         const int nbase = base + nwarps * NS;
         Tuple nxt = fetch((nbase > 0 && nbase < n_tuples) ? nbase : -1);
-        TupleScalars ns = {0.f, 0.f, 0.f, 0.f, 0, 0, -1};
+        TupleScalars ns = {0.f, 0.f, 0, 0, -1};
         float* buf = sbuf + flip * BUFF;
         float* nbuf = sbuf + (flip ^ 1) * BUFF;
         cp_async_wait_all();
@@ -684,10 +458,12 @@ __global__ void __launch_bounds__(256, MINB) fast_warp_v4_kernel(FitArgs a, cons
             const size_t on = (size_t)(upd ? neg_id : 0) * D;
             float4 gn[VPL];
             float nbg = 1.0f;
-            if (upd) {  // the only fetches left on the critical path
+            if (upd) {  // the only fetches left on the critical path, all issued together
 #pragma unroll
                 for (int v = 0; v < VPL; v++) gn[v] = ldcg4(m.item.g + on + (sub + LPR * v) * 4);
-                if (sub == 1) nbg = __ldcg(m.item.bg + neg_id);
+                if (sub < 3)  // bias accumulators: sub 0 positive, 1 negative, 2 user
+                    nbg = __ldcg(sub == 0 ? m.item.bg + cur.item : sub == 1 ? m.item.bg + neg_id
+                                                                             : m.user.bg + cur.user);
             }
             if (upd) {
                 const size_t op = (size_t)cur.item * D, ou = (size_t)cur.user * D;
@@ -706,7 +482,7 @@ __global__ void __launch_bounds__(256, MINB) fast_warp_v4_kernel(FitArgs a, cons
                 if (sub < 3) {  // biases: sub 0 positive (-loss), 1 negative (+loss), 2 user (+loss)
                     float* b = sub == 0 ? m.item.b + cur.item : sub == 1 ? m.item.b + neg_id : m.user.b + cur.user;
                     float* bg = sub == 0 ? m.item.bg + cur.item : sub == 1 ? m.item.bg + neg_id : m.user.bg + cur.user;
-                    const float g0 = sub == 0 ? cs.pbg : sub == 1 ? nbg : cs.ubg;
+                    const float g0 = nbg;
                     const float g = sub == 0 ? -loss : loss;
                     red_add(b, -lr * rsqrt_ftz(g0) * g);
                     red_add(bg, g * g);
@@ -849,27 +625,6 @@ FastGrid fast_grid(K kernel, int64_t warps_wanted, int64_t warps_cap) {
     return g;
 }
 
-template <int LPR, int MINB>
-cudaError_t launch_warp_v2(const FitArgs& b, const Tuple* tp, int64_t count, cudaStream_t st) {
-    constexpr int D = 4 * LPR;
-    const size_t smem = (size_t)8 * 2 * 4 * D * sizeof(float);
-    auto kern = fast_warp_v2_kernel<LPR, MINB>;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
-    if (per_sm < 1) per_sm = 1;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int64_t blocks = (int64_t)sms * per_sm;
-    int64_t need = (count + 7) / 8, cap = (lfm_inflight_cap(count) + 7) / 8;
-    if (blocks > need) blocks = need;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    kern<<<(int)blocks, 256, smem, st>>>(b, tp);
-    return cudaGetLastError();
-}
-
 template <int D, int VPL, int MINB>
 cudaError_t launch_warp_v4(const FitArgs& b, const Tuple* tp, int64_t count, cudaStream_t st) {
     constexpr int LPR = D / (4 * VPL);
@@ -893,7 +648,7 @@ cudaError_t launch_warp_v4(const FitArgs& b, const Tuple* tp, int64_t count, cud
     return cudaGetLastError();
 }
 
-// 0: v1 (warp per interaction); 1/2/3: v2 pipelined at 4/5/6 CTAs per SM;
+// 0: v1 (warp per interaction, speculative negatives);
 // 4/5: v4 (slot per interaction, 1 chunk per lane) at 3/4 CTAs per SM;
 // 6/7/8: v5 (2 chunks per lane, twice the interactions per warp; d >= 32) at 2/3/4 CTAs per SM
 static int g_tuning = 7;
@@ -905,9 +660,6 @@ cudaError_t launch_fast(const FitArgs& a, const Tuple* tuples, int64_t begin, in
     b.n = count;
     const Tuple* tp = tuples + begin;
     if constexpr (LOSS == LOSS_WARP) {
-        if (g_tuning == 1) return launch_warp_v2<LPR, 4>(b, tp, count, st);
-        if (g_tuning == 2) return launch_warp_v2<LPR, 5>(b, tp, count, st);
-        if (g_tuning == 3) return launch_warp_v2<LPR, 6>(b, tp, count, st);
         constexpr int DD = 4 * LPR;
         if (g_tuning == 4) return launch_warp_v4<DD, 1, 3>(b, tp, count, st);
         if (g_tuning == 5) return launch_warp_v4<DD, 1, 4>(b, tp, count, st);
@@ -948,7 +700,7 @@ cudaError_t launch_fast_d(const FitArgs& a, const Tuple* tuples, int64_t begin, 
 
 extern "C" int lfm_set_tuning(int variant) {
     int old = g_tuning;
-    if (variant >= 0 && variant <= 8) g_tuning = variant;
+    if (variant == 0 || (variant >= 4 && variant <= 8)) g_tuning = variant;
     return old;
 }
 

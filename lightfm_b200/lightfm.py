@@ -270,8 +270,9 @@ class LightFM(object):
         """Throughput mode: upload the problem once, run all epochs on the device
         (SURVEY 8(f) row 1).  The reference re-builds the positives CSR, re-shuffles on the host
         and re-crosses the boundary with every array once per epoch (L:668-759); here each epoch
-        consumes ONE ``random_state.randint`` draw (the key of the device-side permutation and
-        of the Philox negative sampler), so the caller's RandomState still advances every epoch.
+        consumes one block of ``random_state.randint`` draws (folded into the key of the device-side
+        permutation and of the Philox negative sampler), so the caller's RandomState still
+        advances every epoch.
         The numpy state arrays are written back once at the end (or before raising)."""
         pairwise = self.loss in ("warp", "bpr", "warp-kos")
         positives = _native.CSRMatrix(self._positives_lookup(interactions)) if pairwise else None
@@ -283,7 +284,11 @@ class LightFM(object):
             self.user_alpha, self.k, self.n)
         try:
             for _ in self._progress(epochs, verbose=verbose):
-                seed = self.random_state.randint(0, np.iinfo(np.int32).max)
+                # 625 words: one full Mersenne-Twister block, so get_state()[1] changes every
+                # epoch as it does under the reference's per-epoch shuffle
+                # (reference tests/test_movielens.py:669-682)
+                words = self.random_state.randint(0, np.iinfo(np.int32).max, size=625)
+                seed = int(np.bitwise_xor.reduce(words.astype(np.uint32) * np.uint32(2654435761)))
                 plan.epoch(seed, num_threads=max(2, num_threads))
                 if not plan.all_finite():
                     break

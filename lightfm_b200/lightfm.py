@@ -367,13 +367,50 @@ class LightFM(object):
 
         n_users = user_ids.max() + 1
         n_items = item_ids.max() + 1
+        identity = user_features is None and item_features is None
         user_features, item_features = self._construct_feature_matrices(
             n_users, n_items, user_features, item_features)
+
+        if identity:
+            compact = self._predict_compact(user_ids, item_ids, num_threads)
+            if compact is not None:
+                return compact
 
         predictions = np.empty(len(user_ids), dtype=np.float32)
         _native.predict_lightfm(_native.CSRMatrix(item_features), _native.CSRMatrix(user_features),
                                 np.ascontiguousarray(user_ids), np.ascontiguousarray(item_ids),
                                 predictions, self._get_lightfm_data(), num_threads)
+        return predictions
+
+    def _predict_compact(self, user_ids, item_ids, num_threads):
+        """Small batches with identity features: the native call stages the whole model on the
+        device, which dominates when only a few rows are needed (the reference's own tests and
+        docs call ``predict`` once per user).  Gather just the rows the batch touches into a
+        compact model on the host and score that -- same kernel, same arithmetic, bit-identical
+        scores.  Returns None when the batch touches a large part of the tables."""
+        uu, ui = np.unique(user_ids, return_inverse=True)
+        iu, ii = np.unique(item_ids, return_inverse=True)
+        if 4 * (len(uu) + len(iu)) >= self.user_embeddings.shape[0] + self.item_embeddings.shape[0]:
+            return None
+        d = self.no_components
+
+        def side(emb, bias, ids):
+            e = np.ascontiguousarray(emb[ids])
+            b = np.ascontiguousarray(bias[ids])
+            z, zb = np.zeros_like(e), np.zeros_like(b)
+            return [e, z, z.copy(), b, zb, zb.copy()]
+
+        state = _native.FastLightFM(
+            *(side(self.item_embeddings, self.item_biases, iu)
+              + side(self.user_embeddings, self.user_biases, uu)),
+            d, int(self.learning_schedule == "adadelta"), self.learning_rate, self.rho, self.epsilon,
+            self.max_sampled)
+        predictions = np.empty(len(user_ids), dtype=np.float32)
+        _native.predict_lightfm(
+            _native.CSRMatrix(sp.identity(len(iu), dtype=CYTHON_DTYPE, format="csr")),
+            _native.CSRMatrix(sp.identity(len(uu), dtype=CYTHON_DTYPE, format="csr")),
+            np.ascontiguousarray(ui.astype(np.int32)), np.ascontiguousarray(ii.astype(np.int32)),
+            predictions, state, num_threads)
         return predictions
 
     @staticmethod

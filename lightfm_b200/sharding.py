@@ -116,3 +116,120 @@ class CudaArrayView(object):
     def __init__(self, ptr, count, dtype="<f4"):
         self.__cuda_array_interface__ = {
             "shape": (int(count),), "typestr": dtype, "data": (int(ptr), False), "version": 2}
+
+
+class ShardedTrainer(object):
+    """Hogwild training of one ``LightFM`` problem across the ranks of a torch.distributed
+    group (one process per GPU, launched by torchrun).
+
+    Every rank calls it with the SAME global interactions and an identically initialised
+    model (same ``random_state``); the trainer keeps this rank's shard of the sharded table and
+    a replica of the other table resident in HBM (``ResidentPlan``), runs local epochs with the
+    single-GPU kernels and all-reduces the replicated table's delta after every epoch.
+
+        model = LightFM(loss="warp", no_components=64, random_state=0)
+        trainer = ShardedTrainer(model, interactions, axis="item")      # under torchrun
+        trainer.fit_epochs(10)
+        trainer.gather()          # every rank's model arrays now hold the full trained state
+
+    Identity features only (see module docstring).
+    """
+
+    REPLICATED_TABLES = {"item": (6, 7, 9, 10), "user": (0, 1, 3, 4)}  # lfm_plan_table ids: w, g, b, bg
+
+    def __init__(self, model, interactions, axis="item", sample_weight=None, group=None, device=None):
+        import torch
+        import torch.distributed as dist
+        from . import _lightfm_fast as native
+        if model.learning_schedule != "adagrad":
+            raise NotImplementedError("ShardedTrainer supports the adagrad schedule")
+        self.model, self.axis, self.group = model, axis, group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        coo = interactions.tocoo()
+        if coo.dtype != np.float32:
+            coo.data = coo.data.astype(np.float32)
+        self.shape = coo.shape
+        n_users, n_items = coo.shape
+        if model.item_embeddings is None:
+            model._initialize(model.no_components, n_items, n_users)
+        local, weight, positives, self.smap = partition(coo, sample_weight, axis, self.rank, self.world)
+        if weight is None:
+            weight = local.data if np.array_equiv(local.data, 1.0) else np.ones_like(local.data)
+        self._global = {k: getattr(model, k) for k in _STATE_NAMES}
+        self.local_state = slice_state(self._global, axis, self.smap)
+        st = self.local_state
+        self._holder = native.FastLightFM(
+            *[st[k] for k in _STATE_NAMES], model.no_components, 0, model.learning_rate, model.rho,
+            model.epsilon, model.max_sampled)
+        lu, li = local.shape
+        kos = model.loss == "warp-kos"
+        self._keep = (local, weight, positives)
+        self.plan = native.ResidentPlan(
+            model.loss, native.CSRMatrix(sp.identity(li, dtype=np.float32, format="csr")),
+            native.CSRMatrix(sp.identity(lu, dtype=np.float32, format="csr")),
+            native.CSRMatrix(positives) if model.loss != "logistic" else None,
+            np.ascontiguousarray(local.row), None if kos else np.ascontiguousarray(local.col),
+            None if kos else local.data, None if kos else weight, self._holder,
+            model.item_alpha, model.user_alpha, model.k, model.n)
+        if axis == "item":
+            self.plan.set_global_items(n_items)
+        import torch as _t
+        self.views = [_t.as_tensor(CudaArrayView(*self.plan.table(w)), device=self.device)
+                      for w in self.REPLICATED_TABLES[axis]]
+        self.local_interactions = local.nnz
+        self.last_counters = None
+
+    def epoch(self, seed, num_threads=8):
+        """One local epoch + the delta all-reduce of the replicated table."""
+        import torch
+        snaps = [v.clone() for v in self.views]
+        torch.cuda.synchronize(self.device)
+        c = self.plan.epoch(seed=(int(seed) * 977 + self.rank) & 0xFFFFFFFF, num_threads=max(2, num_threads))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        if self.world > 1:
+            allreduce_deltas(self.views, snaps, self.group)
+        e1.record()
+        torch.cuda.synchronize(self.device)
+        c["allreduce_ms"] = e0.elapsed_time(e1)
+        self.last_counters = c
+        return c
+
+    def fit_epochs(self, epochs, num_threads=8):
+        for _ in range(epochs):
+            seed = int(self.model.random_state.randint(0, np.iinfo(np.int32).max))
+            self.epoch(seed, num_threads)
+        return self
+
+    def gather(self):
+        """Write the trained state back into the model's (global) numpy arrays on every rank:
+        the replicated side from the local replica, the sharded side by all-gathering shards."""
+        import torch
+        import torch.distributed as dist
+        self.plan.download()
+        merge_state(self._global, self.local_state, self.axis, self.smap)
+        if self.world > 1:
+            side = "item" if self.axis == "item" else "user"
+            n_global = self.shape[1] if self.axis == "item" else self.shape[0]
+            owner = shard_of(np.arange(n_global, dtype=np.int64), self.world)
+            for k in _STATE_NAMES:
+                if not k.startswith(side):
+                    continue
+                arr = self._global[k]
+                t = torch.from_numpy(arr).to(self.device)
+                mask = torch.from_numpy((owner == self.rank)).to(self.device)
+                t = t * (mask.view(-1, *([1] * (t.dim() - 1)))).to(t.dtype)  # zero the rows of other shards
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+                arr[...] = t.cpu().numpy()
+        return self.model
+
+    def close(self):
+        self.plan.close()
+
+
+_STATE_NAMES = ("item_embeddings", "item_embedding_gradients", "item_embedding_momentum",
+                "item_biases", "item_bias_gradients", "item_bias_momentum",
+                "user_embeddings", "user_embedding_gradients", "user_embedding_momentum",
+                "user_biases", "user_bias_gradients", "user_bias_momentum")

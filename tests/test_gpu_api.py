@@ -109,3 +109,23 @@ def test_user_mutation_between_calls_is_respected():
     p = model.predict(0, np.arange(60, dtype=np.int32))
     emb = model.user_embeddings[0] @ model.item_embeddings.T + model.user_biases[0] + 5.0
     assert np.allclose(p, emb, atol=1e-5)
+
+
+def test_sharded_trainer_single_rank_matches_plain_fit_statistically():
+    """ShardedTrainer with one rank (no process group) is the plain resident path: it must learn
+    the planted structure as well as LightFM.fit does, and gather() must fill the model arrays."""
+    from lightfm_b200 import sharding
+    full = H.planted_interactions(400, 300, 30, seed=5)
+    train, test = H.split(full, 7)
+    model = LightFM(loss="warp", no_components=32, random_state=1)
+    trainer = sharding.ShardedTrainer(model, train, axis="item")
+    assert trainer.world == 1 and trainer.local_interactions == train.nnz
+    trainer.fit_epochs(8)
+    trainer.gather()
+    trainer.close()
+    arrays = {k: getattr(model, k) for k in H.MODEL_ARRAYS}
+    p, auc = H.eval_arrays(arrays, 32, train, test)
+    plain = LightFM(loss="warp", no_components=32, random_state=1).fit(train, epochs=8, num_threads=8)
+    p2, auc2 = H.eval_arrays({k: getattr(plain, k) for k in H.MODEL_ARRAYS}, 32, train, test)
+    assert auc > 0.65 and abs(auc - auc2) < 0.03, (auc, auc2)
+    assert np.all(model.item_embedding_gradients >= 1) and np.any(model.user_embedding_gradients > 1)

@@ -157,3 +157,18 @@ def test_adadelta_hogwild_learns():
     arr = _fit(cu, "warp", train, 32, 8, 0, 8, schedule="adadelta")
     p, auc = H.eval_arrays(arr, 32, train, test)
     assert auc > 0.65
+
+
+def test_midscale_hogwild_matches_oracle_heldout_metrics():
+    """~0.6 M interactions (full B200 wave in flight: 4.7 k warps, no in-flight cap): three epochs
+    of GPU hogwild WARP vs the single-thread oracle on planted low-rank data."""
+    cu, orc = H.cuda_native(), H.oracle_native()
+    full = H.planted_interactions(12000, 4000, 60, seed=11)
+    train, test = H.split(full, 5, frac=0.85)
+    res = []
+    for api, nt in ((orc, 1), (cu, 8)):
+        arr = _fit(api, "warp", train, 64, 3, 0, nt)
+        res.append(H.eval_arrays(arr, 64, train, test))
+    assert res[0][1] > 0.7 and res[1][1] > 0.7, res
+    assert abs(res[0][1] - res[1][1]) < 0.02, res
+    assert abs(res[0][0] - res[1][0]) <= 0.12 * res[0][0] + 0.005, res

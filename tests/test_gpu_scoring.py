@@ -162,3 +162,23 @@ def test_in_positives_known_answers():  # reference tests/test_fast_functions.py
     present = set(cols.tolist())
     for col in list(cols[:40]) + list(cols[-40:]) + rng.integers(0, 100000, 80).tolist():
         assert cu.test_in_positives(0, int(col), c) == (int(col) in present)
+
+
+def test_compact_predict_is_bit_identical_to_full_predict():
+    """predict() on a small batch gathers only the touched rows (LightFM._predict_compact); the
+    scores must equal the full-model path bit for bit."""
+    from lightfm_b200 import LightFM, _lightfm_fast as fast
+    inter = H.synthetic_interactions(3000, 2000, 40000, 9)
+    model = LightFM(loss="bpr", no_components=24, random_state=3).fit(inter, epochs=1, num_threads=4)
+    rng = np.random.default_rng(0)
+    u = rng.integers(0, 3000, 200).astype(np.int32)
+    i = rng.integers(0, 2000, 200).astype(np.int32)
+    assert model._predict_compact(u, i, 1) is not None
+    got = model.predict(u, i)
+    full = np.empty(200, np.float32)
+    fast.predict_lightfm(fast.CSRMatrix(sp.identity(2000, dtype=np.float32, format="csr")),
+                         fast.CSRMatrix(sp.identity(3000, dtype=np.float32, format="csr")),
+                         u, i, full, model._get_lightfm_data(), 1)
+    assert np.array_equal(got, full)
+    assert np.array_equal(model.predict(7, np.arange(50, dtype=np.int32)),
+                          model.predict(np.repeat(7, 50).astype(np.int32), np.arange(50, dtype=np.int32)))

@@ -189,6 +189,8 @@ int lfm_test_in_positives(int32_t row, int32_t col, const lfm_csr *mat);
  * 2 bpr, 3 warp-kos.  `interactions` is the sorted positives CSR (NULL for logistic);
  * item_ids / Y / sample_weight are NULL for warp-kos.                                  */
 typedef struct lfm_plan lfm_plan;
+/* *out must be NULL (new plan) or an existing plan, which is then refreshed in place: all inputs
+ * and the model are uploaded again into the plan's existing device buffers. */
 int lfm_plan_create(lfm_plan **out, int32_t loss, const lfm_csr *item_features,
                     const lfm_csr *user_features, const lfm_csr *interactions,
                     const int32_t *user_ids, const int32_t *item_ids, const float *Y,

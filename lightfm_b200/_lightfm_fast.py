@@ -143,8 +143,18 @@ class ResidentPlan(object):
     def __init__(self, loss, item_features, user_features, interactions, user_ids, item_ids, Y,
                  sample_weight, lightfm, item_alpha, user_alpha, k=5, n=10):
         self._handle = ctypes.c_void_p()
+        self._args = (loss, item_features, user_features, interactions, user_ids, item_ids, Y,
+                      sample_weight, lightfm, item_alpha, user_alpha, k, n)
+        self._upload()
+
+    def refresh(self):
+        """Upload every input and the model again into the plan's existing device buffers."""
+        self._upload()
+
+    def _upload(self):
+        (loss, item_features, user_features, interactions, user_ids, item_ids, Y, sample_weight,
+         lightfm, item_alpha, user_alpha, k, n) = self._args
         self._lightfm = lightfm
-        self._keep = (item_features, user_features, interactions, user_ids, item_ids, Y, sample_weight)
         n_ex = len(user_ids)
         null_i = ctypes.cast(None, _abi.c_i32p)
         null_f = ctypes.cast(None, _abi.c_f32p)

@@ -700,7 +700,9 @@ extern "C" int lfm_plan_create(lfm_plan** out, int32_t loss, const lfm_csr* item
     if (loss < LOSS_LOGISTIC || loss > LOSS_KOS) return fail(LFM_ERR_ARG, "bad loss %d", loss);
     int rc = ensure_init();
     if (rc != LFM_OK) return rc;
-    lfm_plan* p = new lfm_plan();
+    // *out != NULL: refresh an existing plan in place (same device buffers, everything re-uploaded)
+    const bool reuse = *out != nullptr;
+    lfm_plan* p = reuse ? *out : new lfm_plan();
     p->loss = loss;
     p->nkos = n;
     g_cur = &p->arena;
@@ -714,9 +716,11 @@ extern "C" int lfm_plan_create(lfm_plan** out, int32_t loss, const lfm_csr* item
     }
     g_cur = &g_arena;
     if (rc != LFM_OK) {
-        for (auto& kv : p->arena)
-            if (kv.second.p) cudaFree(kv.second.p);
-        delete p;
+        if (!reuse) {
+            for (auto& kv : p->arena)
+                if (kv.second.p) cudaFree(kv.second.p);
+            delete p;
+        }
         return rc;
     }
     *out = p;

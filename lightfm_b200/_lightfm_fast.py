@@ -91,9 +91,9 @@ def set_tuning(variant):
     return fn(int(variant))
 
 
-_TUNING_NAMES = {0: "fast_rank_kernel<WARP,LPR=d/4>", 4: "fast_warp_v4_kernel<d,1,3>", 5: "fast_warp_v4_kernel<d,1,4>",
-                 6: "fast_warp_v4_kernel<d,2,2>", 7: "fast_warp_v4_kernel<d,2,3>",
-                 8: "fast_warp_v4_kernel<d,2,4>"}
+_TUNING_NAMES = {0: "fast_rank_kernel<WARP,LPR=d/4>", 4: "fast_slot_kernel<WARP,d,1,3>", 5: "fast_slot_kernel<WARP,d,1,4>",
+                 6: "fast_slot_kernel<WARP,d,2,2>", 7: "fast_slot_kernel<WARP,d,2,3>",
+                 8: "fast_slot_kernel<WARP,d,2,4>"}
 
 
 def warp_kernel_name(d=64):

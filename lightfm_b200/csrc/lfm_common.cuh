@@ -67,7 +67,8 @@ struct FitArgs {
     const float* y;
     const float* sample_weight;
     const int32_t* shuffle;        // host-provided order, or null -> device permutation
-    int64_t n;                     // no_examples
+    int64_t n;                     // no_examples of this launch (an epoch segment)
+    int64_t n_all;                 // no_examples of the whole epoch (BPR draws negatives from all of it)
     double item_alpha, user_alpha;
     int32_t k, nkos;               // k-OS parameters
     uint32_t seed;                 // rand_r seed (replay) / philox key (hogwild)

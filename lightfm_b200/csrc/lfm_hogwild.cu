@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(256) hogwild_kernel(FitArgs a, const Tuple* __
             if (LOSS == LOSS_BPR) {
                 int tries = 0;
                 do {  // T:1123-1127: popularity-weighted draw from the interaction list
-                    int64_t j = (int64_t)(((unsigned long long)next_u32() * (unsigned long long)a.n) >> 32);
+                    int64_t j = (int64_t)(((unsigned long long)next_u32() * (unsigned long long)a.n_all) >> 32);
                     neg_id = __ldg(a.item_ids + j);
                     c_neg++;
                     tries++;

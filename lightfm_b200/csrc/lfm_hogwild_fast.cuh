@@ -241,7 +241,7 @@ struct TupleScalars {
     int probe;       // lane's first-level probe of that row (key independent, see slot_member)
 };
 
-// ---- WARP, one SLOT per interaction (v4/v5) --------------------------------------
+// ---- WARP / BPR / logistic: one SLOT per interaction --------------------------------------
 // ncu (profiles/r1_ncu_v3_summary.txt): once the dependent-load chain of the warp-per-interaction
 // kernel was pipelined it became
 // issue-bound (66% issue-active, ~600 warp-instructions per interaction), because with one
@@ -333,8 +333,10 @@ __device__ __forceinline__ int slot_probe_index(int lo, int hi, int sub) {
     return lo + (int)(((unsigned long long)(unsigned)len * (unsigned)sub) >> LOG);
 }
 
-template <int D, int VPL, int MINB>
-__global__ void __launch_bounds__(256, MINB) fast_warp_v4_kernel(FitArgs a, const Tuple* __restrict__ tuples) {
+template <int LOSS, int D, int VPL, int MINB>
+__global__ void __launch_bounds__(256, MINB) fast_slot_kernel(FitArgs a, const Tuple* __restrict__ tuples) {
+    static_assert(LOSS == LOSS_WARP || LOSS == LOSS_BPR || LOSS == LOSS_LOGISTIC, "k-OS uses fast_rank_kernel");
+    constexpr bool PAIRWISE = LOSS != LOSS_LOGISTIC;  // has a negative item and a positives CSR
     constexpr int LPR = D / (4 * VPL);
     constexpr int NS = 32 / LPR;
     constexpr int BUFF = 4 * D;  // floats per slot per buffer: u, p, Gu, Gp rows
@@ -366,10 +368,12 @@ __global__ void __launch_bounds__(256, MINB) fast_warp_v4_kernel(FitArgs a, cons
         }
         sc.ub = __ldcg(m.user.b + tp.user);
         sc.pb = __ldcg(m.item.b + tp.item);
-        sc.ps = __ldg(a.pos.indptr + tp.user);
-        sc.pe = __ldg(a.pos.indptr + tp.user + 1);
-        const int pi = slot_probe_index<LPR>(sc.ps, sc.pe, sub);
-        sc.probe = pi >= 0 ? __ldg(a.pos.indices + pi) : -1;
+        if (PAIRWISE) {
+            sc.ps = __ldg(a.pos.indptr + tp.user);
+            sc.pe = __ldg(a.pos.indptr + tp.user + 1);
+            const int pi = slot_probe_index<LPR>(sc.ps, sc.pe, sub);
+            sc.probe = pi >= 0 ? __ldg(a.pos.indices + pi) : -1;
+        }
     };
     auto fetch = [&](int base) -> Tuple {
         Tuple tp = {-1, 0, 0.0f, 0.0f};
@@ -407,44 +411,81 @@ __global__ void __launch_bounds__(256, MINB) fast_warp_v4_kernel(FitArgs a, cons
         }
         pp = slot_sum<LPR>(pp) + cs.ub + cs.pb;
 
-        // ---- rank sampling (T:855-899): every slot draws its own candidates in lockstep ----
         int sampled = 0, neg_id = -1;
         float loss = 0.0f;
         float4 q[VPL];
 #pragma unroll
         for (int v = 0; v < VPL; v++) q[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-        Philox4 r4 = {0u, 0u, 0u, 0u};
-        bool active = valid && max_sampled > 0;
-        for (int round = 0; __any_sync(LFM_FULL, active); round++) {
-            if ((round & 3) == 0)
-                r4 = philox7((uint32_t)t, 0u, (uint32_t)(round >> 2), 0u, a.seed, 0x4c464d31u);
-            const int w = round & 3;
-            const uint32_t r = w == 0 ? r4.x : w == 1 ? r4.y : w == 2 ? r4.z : r4.w;
-            const int cand = lfm_bounded(r, (uint32_t)n_items);
-            float qb = 0.0f;
-            if (active) {
+
+        if constexpr (LOSS == LOSS_WARP) {
+            // ---- rank sampling (T:855-899): every slot draws its own candidates in lockstep ----
+            Philox4 r4 = {0u, 0u, 0u, 0u};
+            bool active = valid && max_sampled > 0;
+            for (int round = 0; __any_sync(LFM_FULL, active); round++) {
+                if ((round & 3) == 0)
+                    r4 = philox7((uint32_t)t, 0u, (uint32_t)(round >> 2), 0u, a.seed, 0x4c464d31u);
+                const int w = round & 3;
+                const uint32_t r = w == 0 ? r4.x : w == 1 ? r4.y : w == 2 ? r4.z : r4.w;
+                const int cand = lfm_bounded(r, (uint32_t)n_items);
+                float qb = 0.0f;
+                if (active) {
 #pragma unroll
-                for (int v = 0; v < VPL; v++) q[v] = ldcg4(m.item.w + (size_t)cand * D + (sub + LPR * v) * 4);
-                qb = __ldcg(m.item.b + cand);
+                    for (int v = 0; v < VPL; v++) q[v] = ldcg4(m.item.w + (size_t)cand * D + (sub + LPR * v) * 4);
+                    qb = __ldcg(m.item.b + cand);
+                }
+                float part = 0.0f;
+#pragma unroll
+                for (int v = 0; v < VPL; v++) part += dot4(u[v], q[v]);
+                const float np = slot_sum<LPR>(part) + cs.ub + qb;
+                const bool viol = active && np > pp - 1.0f;
+                const bool member = slot_member<LPR>(a.pos.indices, cs.ps, cs.pe, cs.probe, cand, viol, sub, slotmask);
+                if (active) {
+                    sampled++;
+                    if (viol) {
+                        if (member) {
+                            if (sub == 0) c_rej++;
+                        } else {
+                            neg_id = cand;
+                            loss = fminf(cur.weight * (float)a.loss_table[sampled], (float)LFM_MAX_LOSS);
+                        }
+                    }
+                    active = neg_id < 0 && sampled < max_sampled;
+                }
+            }
+        } else if constexpr (LOSS == LOSS_BPR) {
+            // ---- T:1123-1127: popularity-weighted draw from the interaction list until it is
+            //      not one of the user's positives (almost always the first try) ----
+            Philox4 r4 = {0u, 0u, 0u, 0u};
+            bool active = valid;
+            for (int round = 0; __any_sync(LFM_FULL, active); round++) {
+                if ((round & 3) == 0)
+                    r4 = philox7((uint32_t)t, 0u, (uint32_t)(round >> 2), 2u, a.seed, 0x4c464d31u);
+                const int w = round & 3;
+                const uint32_t r = w == 0 ? r4.x : w == 1 ? r4.y : w == 2 ? r4.z : r4.w;
+                const int64_t j = (int64_t)(((unsigned long long)r * (unsigned long long)a.n_all) >> 32);
+                const int cand = active ? __ldg(a.item_ids + j) : 0;
+                const bool member = slot_member<LPR>(a.pos.indices, cs.ps, cs.pe, cs.probe, cand, active, sub, slotmask);
+                if (active) {
+                    sampled++;
+                    neg_id = cand;
+                    if (member && sub == 0) c_rej++;
+                    active = member && sampled < 256;
+                }
+            }
+            float qb = 0.0f;
+            if (valid) {
+#pragma unroll
+                for (int v = 0; v < VPL; v++) q[v] = ldcg4(m.item.w + (size_t)neg_id * D + (sub + LPR * v) * 4);
+                qb = __ldcg(m.item.b + neg_id);
             }
             float part = 0.0f;
 #pragma unroll
             for (int v = 0; v < VPL; v++) part += dot4(u[v], q[v]);
             const float np = slot_sum<LPR>(part) + cs.ub + qb;
-            const bool viol = active && np > pp - 1.0f;
-            const bool member = slot_member<LPR>(a.pos.indices, cs.ps, cs.pe, cs.probe, cand, viol, sub, slotmask);
-            if (active) {
-                sampled++;
-                if (viol) {
-                    if (member) {
-                        if (sub == 0) c_rej++;
-                    } else {
-                        neg_id = cand;
-                        loss = fminf(cur.weight * (float)a.loss_table[sampled], (float)LFM_MAX_LOSS);
-                    }
-                }
-                active = neg_id < 0 && sampled < max_sampled;
-            }
+            loss = cur.weight * (1.0f - 1.0f / (1.0f + __expf(-(pp - np))));
+        } else {  // logistic, T:747-759
+            const float pred = 1.0f / (1.0f + __expf(-pp));
+            loss = cur.weight * (pred - (cur.y > 0 ? 1.0f : 0.0f));
         }
         if (valid && sub == 0) { c_pos++; c_neg += sampled; }
 
@@ -452,18 +493,22 @@ __global__ void __launch_bounds__(256, MINB) fast_warp_v4_kernel(FitArgs a, cons
         stage(nxt, nbuf, ns);
         cp_async_commit();
 
-        // ---- update (T:537-649): three rows + three biases per slot, one instruction stream ----
-        const bool upd = neg_id >= 0;
+        // ---- update (T:454-534 / T:537-649): rows + biases of a slot, one instruction stream ----
+        const bool upd = LOSS == LOSS_WARP ? neg_id >= 0 : valid;
         if (__any_sync(LFM_FULL, upd)) {
-            const size_t on = (size_t)(upd ? neg_id : 0) * D;
             float4 gn[VPL];
-            float nbg = 1.0f;
-            if (upd) {  // the only fetches left on the critical path, all issued together
+            float bgv = 1.0f;  // bias accumulator: sub 0 item (positive), 1 negative / user, 2 user
+            if (upd) {         // the only fetches left on the critical path, all issued together
+                if constexpr (PAIRWISE) {
+                    const size_t on = (size_t)neg_id * D;
 #pragma unroll
-                for (int v = 0; v < VPL; v++) gn[v] = ldcg4(m.item.g + on + (sub + LPR * v) * 4);
-                if (sub < 3)  // bias accumulators: sub 0 positive, 1 negative, 2 user
-                    nbg = __ldcg(sub == 0 ? m.item.bg + cur.item : sub == 1 ? m.item.bg + neg_id
-                                                                             : m.user.bg + cur.user);
+                    for (int v = 0; v < VPL; v++) gn[v] = ldcg4(m.item.g + on + (sub + LPR * v) * 4);
+                    if (sub < 3)
+                        bgv = __ldcg(sub == 0 ? m.item.bg + cur.item : sub == 1 ? m.item.bg + neg_id
+                                                                                 : m.user.bg + cur.user);
+                } else {
+                    if (sub < 2) bgv = __ldcg(sub == 0 ? m.item.bg + cur.item : m.user.bg + cur.user);
+                }
             }
             if (upd) {
                 const size_t op = (size_t)cur.item * D, ou = (size_t)cur.user * D;
@@ -474,18 +519,33 @@ __global__ void __launch_bounds__(256, MINB) fast_warp_v4_kernel(FitArgs a, cons
                     const float4 gu = *(const float4*)(buf + 2 * D + o);
                     const float4 gp = *(const float4*)(buf + 3 * D + o);
                     const float lx = loss * u[v].x, ly = loss * u[v].y, lz = loss * u[v].z, lw = loss * u[v].w;
-                    adagrad_row4_g(m.item.w + op + o, m.item.g + op + o, gp, lr, -lx, -ly, -lz, -lw);
-                    adagrad_row4_g(m.user.w + ou + o, m.user.g + ou + o, gu, lr, loss * (q[v].x - p4.x),
-                                   loss * (q[v].y - p4.y), loss * (q[v].z - p4.z), loss * (q[v].w - p4.w));
-                    adagrad_row4_g(m.item.w + on + o, m.item.g + on + o, gn[v], lr, lx, ly, lz, lw);
+                    if constexpr (PAIRWISE) {
+                        const size_t on = (size_t)neg_id * D;
+                        adagrad_row4_g(m.item.w + op + o, m.item.g + op + o, gp, lr, -lx, -ly, -lz, -lw);
+                        adagrad_row4_g(m.user.w + ou + o, m.user.g + ou + o, gu, lr, loss * (q[v].x - p4.x),
+                                       loss * (q[v].y - p4.y), loss * (q[v].z - p4.z), loss * (q[v].w - p4.w));
+                        adagrad_row4_g(m.item.w + on + o, m.item.g + on + o, gn[v], lr, lx, ly, lz, lw);
+                    } else {
+                        adagrad_row4_g(m.item.w + op + o, m.item.g + op + o, gp, lr, lx, ly, lz, lw);
+                        adagrad_row4_g(m.user.w + ou + o, m.user.g + ou + o, gu, lr, loss * p4.x, loss * p4.y,
+                                       loss * p4.z, loss * p4.w);
+                    }
                 }
-                if (sub < 3) {  // biases: sub 0 positive (-loss), 1 negative (+loss), 2 user (+loss)
-                    float* b = sub == 0 ? m.item.b + cur.item : sub == 1 ? m.item.b + neg_id : m.user.b + cur.user;
-                    float* bg = sub == 0 ? m.item.bg + cur.item : sub == 1 ? m.item.bg + neg_id : m.user.bg + cur.user;
-                    const float g0 = nbg;
-                    const float g = sub == 0 ? -loss : loss;
-                    red_add(b, -lr * rsqrt_ftz(g0) * g);
-                    red_add(bg, g * g);
+                if constexpr (PAIRWISE) {
+                    if (sub < 3) {  // biases: sub 0 positive (-loss), 1 negative (+loss), 2 user (+loss)
+                        float* b = sub == 0 ? m.item.b + cur.item : sub == 1 ? m.item.b + neg_id : m.user.b + cur.user;
+                        float* bg = sub == 0 ? m.item.bg + cur.item : sub == 1 ? m.item.bg + neg_id : m.user.bg + cur.user;
+                        const float g = sub == 0 ? -loss : loss;
+                        red_add(b, -lr * rsqrt_ftz(bgv) * g);
+                        red_add(bg, g * g);
+                    }
+                } else {
+                    if (sub < 2) {  // biases: sub 0 item, 1 user, both +loss
+                        float* b = sub == 0 ? m.item.b + cur.item : m.user.b + cur.user;
+                        float* bg = sub == 0 ? m.item.bg + cur.item : m.user.bg + cur.user;
+                        red_add(b, -lr * rsqrt_ftz(bgv) * loss);
+                        red_add(bg, loss * loss);
+                    }
                 }
                 if (sub == 0) c_upd++;
             }
@@ -506,101 +566,6 @@ __global__ void __launch_bounds__(256, MINB) fast_warp_v4_kernel(FitArgs a, cons
         atomicAdd(&a.counters->negatives, (unsigned long long)c_neg);
         atomicAdd(&a.counters->updates, (unsigned long long)c_upd);
         atomicAdd(&a.counters->rejected, (unsigned long long)c_rej);
-    }
-}
-
-// ---- logistic and BPR: one slot per interaction ------------------------------
-template <int LOSS, int LPR>
-__global__ void __launch_bounds__(256) fast_pair_kernel(FitArgs a, const Tuple* __restrict__ tuples) {
-    constexpr int D = 4 * LPR;
-    constexpr int NS = 32 / LPR;
-    const int lane = threadIdx.x & 31;
-    const int sub = lane % LPR, slot = lane / LPR;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const DevModel& m = a.model;
-    const float lr = m.lr;
-    unsigned long long c_pos = 0, c_neg = 0, c_upd = 0, c_rej = 0;
-
-    for (int64_t base = warp * NS; base < a.n; base += nwarps * NS) {
-        const int64_t t = base + slot;
-        Tuple tp = {-1, 0, 0.0f, 0.0f};
-        if (t < a.n) tp = tuples[t];
-        const bool act = tp.user >= 0;
-        const int user = act ? tp.user : 0;
-        const int item = act ? tp.item : 0;
-        const float4 u4 = ldcg4(m.user.w + (size_t)user * D + sub * 4);
-        const float ub = __ldcg(m.user.b + user);
-        const float4 p4 = ldcg4(m.item.w + (size_t)item * D + sub * 4);
-        const float pb = __ldcg(m.item.b + item);
-        const float pp = slot_sum<LPR>(dot4(u4, p4)) + ub + pb;
-        if (LOSS == LOSS_LOGISTIC) {
-            const float pred = 1.0f / (1.0f + __expf(-pp));
-            const float loss = tp.weight * (pred - (tp.y > 0 ? 1.0f : 0.0f));
-            if (act) {
-                size_t oi = (size_t)item * D + sub * 4, ou = (size_t)user * D + sub * 4;
-                adagrad_row4(m.item.w + oi, m.item.g + oi, lr, loss * u4.x, loss * u4.y, loss * u4.z,
-                             loss * u4.w);
-                adagrad_row4(m.user.w + ou, m.user.g + ou, lr, loss * p4.x, loss * p4.y, loss * p4.z,
-                             loss * p4.w);
-                if (sub == 0) adagrad_scalar(m.item.b + item, m.item.bg + item, lr, loss);
-                if (sub == 1) adagrad_scalar(m.user.b + user, m.user.bg + user, lr, loss);
-                if (sub == 0) { c_pos++; c_upd++; }
-            }
-        } else {  // BPR, T:1113-1169
-            int neg_id = 0;
-            if (act) {
-                const int ps = __ldg(a.pos.indptr + user), pe = __ldg(a.pos.indptr + user + 1);
-                uint32_t ctr = 0;
-                int rpos = 4;
-                Philox4 r4 = {0u, 0u, 0u, 0u};
-                for (int tries = 0; tries < 256; tries++) {
-                    if (rpos == 4) {
-                        r4 = lfm_philox((uint32_t)t, (uint32_t)(t >> 32), ctr++, 2u, a.seed, 0x4c464d31u);
-                        rpos = 0;
-                    }
-                    uint32_t r = rpos == 0 ? r4.x : rpos == 1 ? r4.y : rpos == 2 ? r4.z : r4.w;
-                    rpos++;
-                    int64_t j = (int64_t)(((unsigned long long)r * (unsigned long long)a.n) >> 32);
-                    neg_id = __ldg(a.item_ids + j);
-                    if (sub == 0) c_neg++;
-                    if (!lfm_bsearch(a.pos.indices, ps, pe, neg_id)) break;
-                    if (sub == 0) c_rej++;
-                }
-            }
-            const float4 n4 = ldcg4(m.item.w + (size_t)neg_id * D + sub * 4);
-            const float nb = __ldcg(m.item.b + neg_id);
-            const float np = slot_sum<LPR>(dot4(u4, n4)) + ub + nb;
-            const float loss = tp.weight * (1.0f - 1.0f / (1.0f + __expf(-(pp - np))));
-            if (act) {
-                size_t op = (size_t)item * D + sub * 4, on = (size_t)neg_id * D + sub * 4,
-                       ou = (size_t)user * D + sub * 4;
-                adagrad_row4(m.item.w + op, m.item.g + op, lr, -loss * u4.x, -loss * u4.y, -loss * u4.z,
-                             -loss * u4.w);
-                adagrad_row4(m.item.w + on, m.item.g + on, lr, loss * u4.x, loss * u4.y, loss * u4.z,
-                             loss * u4.w);
-                adagrad_row4(m.user.w + ou, m.user.g + ou, lr, loss * (n4.x - p4.x), loss * (n4.y - p4.y),
-                             loss * (n4.z - p4.z), loss * (n4.w - p4.w));
-                if (sub == 0) adagrad_scalar(m.item.b + item, m.item.bg + item, lr, -loss);
-                if (sub == 1) adagrad_scalar(m.item.b + neg_id, m.item.bg + neg_id, lr, loss);
-                if (sub == 2) adagrad_scalar(m.user.b + user, m.user.bg + user, lr, loss);
-                if (sub == 0) { c_pos++; c_upd++; }
-            }
-        }
-    }
-    // per-slot counters live on the sub == 0 lanes
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        c_pos += __shfl_xor_sync(LFM_FULL, c_pos, o);
-        c_neg += __shfl_xor_sync(LFM_FULL, c_neg, o);
-        c_upd += __shfl_xor_sync(LFM_FULL, c_upd, o);
-        c_rej += __shfl_xor_sync(LFM_FULL, c_rej, o);
-    }
-    if (lane == 0) {
-        atomicAdd(&a.counters->positives, c_pos);
-        atomicAdd(&a.counters->negatives, c_neg);
-        atomicAdd(&a.counters->updates, c_upd);
-        atomicAdd(&a.counters->rejected, c_rej);
     }
 }
 
@@ -625,12 +590,12 @@ FastGrid fast_grid(K kernel, int64_t warps_wanted, int64_t warps_cap) {
     return g;
 }
 
-template <int D, int VPL, int MINB>
-cudaError_t launch_warp_v4(const FitArgs& b, const Tuple* tp, int64_t count, cudaStream_t st) {
+template <int LOSS, int D, int VPL, int MINB>
+cudaError_t launch_slot(const FitArgs& b, const Tuple* tp, int64_t count, cudaStream_t st) {
     constexpr int LPR = D / (4 * VPL);
     constexpr int NS = 32 / LPR;
     const size_t smem = (size_t)8 * NS * 2 * 4 * D * sizeof(float);
-    auto kern = fast_warp_v4_kernel<D, VPL, MINB>;
+    auto kern = fast_slot_kernel<LOSS, D, VPL, MINB>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
@@ -648,9 +613,11 @@ cudaError_t launch_warp_v4(const FitArgs& b, const Tuple* tp, int64_t count, cud
     return cudaGetLastError();
 }
 
-// 0: v1 (warp per interaction, speculative negatives);
-// 4/5: v4 (slot per interaction, 1 chunk per lane) at 3/4 CTAs per SM;
-// 6/7/8: v5 (2 chunks per lane, twice the interactions per warp; d >= 32) at 2/3/4 CTAs per SM
+// Kernel variant (lfm_set_tuning), measured on C2 in profiles/README.md:
+//   0      fast_rank_kernel for WARP as well (warp per interaction, speculative negatives)
+//   4 / 5  fast_slot_kernel, one float4 per lane, 3 / 4 CTAs per SM
+//   6/7/8  fast_slot_kernel, two float4 per lane (twice the interactions per warp; d >= 32),
+//          2 / 3 / 4 CTAs per SM                                   [7 = default, fastest on C2]
 static int g_tuning = 7;
 
 template <int LOSS, int LPR>
@@ -659,28 +626,34 @@ cudaError_t launch_fast(const FitArgs& a, const Tuple* tuples, int64_t begin, in
     FitArgs b = a;
     b.n = count;
     const Tuple* tp = tuples + begin;
-    if constexpr (LOSS == LOSS_WARP) {
-        constexpr int DD = 4 * LPR;
-        if (g_tuning == 4) return launch_warp_v4<DD, 1, 3>(b, tp, count, st);
-        if (g_tuning == 5) return launch_warp_v4<DD, 1, 4>(b, tp, count, st);
-        if constexpr (DD >= 32) {
-            if (g_tuning == 6) return launch_warp_v4<DD, 2, 2>(b, tp, count, st);
-            if (g_tuning == 7) return launch_warp_v4<DD, 2, 3>(b, tp, count, st);
-            if (g_tuning == 8) return launch_warp_v4<DD, 2, 4>(b, tp, count, st);
-        } else if (g_tuning >= 6) {
-            return launch_warp_v4<DD, 1, 4>(b, tp, count, st);
-        }
-    }
-    if constexpr (LOSS == LOSS_WARP || LOSS == LOSS_KOS) {
+    constexpr int DD = 4 * LPR;
+    if constexpr (LOSS == LOSS_KOS) {
         FastGrid g = fast_grid(fast_rank_kernel<LOSS, LPR>, count, lfm_inflight_cap(count));
         fast_rank_kernel<LOSS, LPR><<<g.blocks, g.threads, 0, st>>>(b, tp);
+        return cudaGetLastError();
     } else {
-        constexpr int NS = 32 / LPR;
-        FastGrid g = fast_grid(fast_pair_kernel<LOSS, LPR>, (count + NS - 1) / NS,
-                               (lfm_inflight_cap(count) + NS - 1) / NS);
-        fast_pair_kernel<LOSS, LPR><<<g.blocks, g.threads, 0, st>>>(b, tp);
+        if constexpr (LOSS == LOSS_WARP) {
+            if (g_tuning == 0) {
+                FastGrid g = fast_grid(fast_rank_kernel<LOSS, LPR>, count, lfm_inflight_cap(count));
+                fast_rank_kernel<LOSS, LPR><<<g.blocks, g.threads, 0, st>>>(b, tp);
+                return cudaGetLastError();
+            }
+        }
+        if constexpr (LOSS != LOSS_WARP) {
+            // no sampling loop to amortise: one float4 per lane at 4 CTAs per SM measured fastest
+            // (C5 logistic: 20.9 ms vs 28.7 ms with two chunks per lane)
+            return launch_slot<LOSS, DD, 1, 4>(b, tp, count, st);
+        }
+        if (g_tuning == 4) return launch_slot<LOSS, DD, 1, 3>(b, tp, count, st);
+        if (g_tuning == 5 || g_tuning == 0) return launch_slot<LOSS, DD, 1, 4>(b, tp, count, st);
+        if constexpr (DD >= 32) {
+            if (g_tuning == 6) return launch_slot<LOSS, DD, 2, 2>(b, tp, count, st);
+            if (g_tuning == 8) return launch_slot<LOSS, DD, 2, 4>(b, tp, count, st);
+            return launch_slot<LOSS, DD, 2, 3>(b, tp, count, st);
+        } else {
+            return launch_slot<LOSS, DD, 1, 4>(b, tp, count, st);
+        }
     }
-    return cudaGetLastError();
 }
 
 template <int LOSS>

@@ -332,6 +332,7 @@ int stage_fit(int loss, const FitInputs& in, bool with_shuffle, Staged* out) {
     a.sample_weight = d_w;
     a.shuffle = d_shuffle;
     a.n = in.n;
+    a.n_all = in.n;
     a.item_alpha = in.item_alpha;
     a.user_alpha = in.user_alpha;
     a.k = in.k;

@@ -57,7 +57,7 @@ __global__ void pack_kernel(const int32_t* __restrict__ user_ids, const int32_t*
         int64_t row = shuffle ? (int64_t)shuffle[i] : feistel_perm(i, n, hb, key);
         Tuple t;
         t.user = user_ids[row];
-        t.item = item_ids ? item_ids[row] : 0;
+        t.item = item_ids ? item_ids[row] : (int32_t)i;  // k-OS: the tuple's index in the epoch
         t.y = y ? y[row] : 1.0f;
         t.weight = w ? w[row] : 1.0f;
         if (skip_nonpositive && !(t.y > 0)) t.user = -1;

@@ -239,6 +239,7 @@ struct TupleScalars {
     float ub, pb;    // user / positive-item bias
     int ps, pe;      // bounds of the user's row in the positives CSR
     int probe;       // lane's first-level probe of that row (key independent, see slot_member)
+    int sid;         // k-OS: the positive item this lane sampled from the user's row
 };
 
 // ---- WARP / BPR / logistic: one SLOT per interaction --------------------------------------
@@ -335,8 +336,9 @@ __device__ __forceinline__ int slot_probe_index(int lo, int hi, int sub) {
 
 template <int LOSS, int D, int VPL, int MINB>
 __global__ void __launch_bounds__(256, MINB) fast_slot_kernel(FitArgs a, const Tuple* __restrict__ tuples) {
-    static_assert(LOSS == LOSS_WARP || LOSS == LOSS_BPR || LOSS == LOSS_LOGISTIC, "k-OS uses fast_rank_kernel");
     constexpr bool PAIRWISE = LOSS != LOSS_LOGISTIC;  // has a negative item and a positives CSR
+    constexpr bool KOS = LOSS == LOSS_KOS;            // positive item chosen in-kernel (T:975-1011)
+    static_assert(!KOS || VPL == 1, "k-OS keeps its sampled positives one per lane: VPL must be 1");
     constexpr int LPR = D / (4 * VPL);
     constexpr int NS = 32 / LPR;
     constexpr int BUFF = 4 * D;  // floats per slot per buffer: u, p, Gu, Gp rows
@@ -362,17 +364,29 @@ __global__ void __launch_bounds__(256, MINB) fast_slot_kernel(FitArgs a, const T
         for (int v = 0; v < VPL; v++) {
             const int o = (sub + LPR * v) * 4;
             cp_async16(buf + 0 * D + o, m.user.w + (size_t)tp.user * D + o);
-            cp_async16(buf + 1 * D + o, m.item.w + (size_t)tp.item * D + o);
             cp_async16(buf + 2 * D + o, m.user.g + (size_t)tp.user * D + o);
-            cp_async16(buf + 3 * D + o, m.item.g + (size_t)tp.item * D + o);
+            if (!KOS) {
+                cp_async16(buf + 1 * D + o, m.item.w + (size_t)tp.item * D + o);
+                cp_async16(buf + 3 * D + o, m.item.g + (size_t)tp.item * D + o);
+            }
         }
         sc.ub = __ldcg(m.user.b + tp.user);
-        sc.pb = __ldcg(m.item.b + tp.item);
+        if (!KOS) sc.pb = __ldcg(m.item.b + tp.item);
         if (PAIRWISE) {
             sc.ps = __ldg(a.pos.indptr + tp.user);
             sc.pe = __ldg(a.pos.indptr + tp.user + 1);
             const int pi = slot_probe_index<LPR>(sc.ps, sc.pe, sub);
             sc.probe = pi >= 0 ? __ldg(a.pos.indices + pi) : -1;
+        }
+        if (KOS) {
+            // lane `sub` draws the sub-th of the min(n, nnz_u) positives sampled with replacement
+            // (T:976-980); the draw only needs the row bounds, so it is prefetched as well.
+            // tp.item carries the tuple's index in the epoch (pack_kernel), the Philox counter.
+            const int len = sc.pe - sc.ps;
+            const Philox4 r4 = philox7((uint32_t)tp.item, 0u, (uint32_t)(sub >> 2), 1u, a.seed, 0x4c464d31u);
+            const uint32_t r = (sub & 3) == 0 ? r4.x : (sub & 3) == 1 ? r4.y : (sub & 3) == 2 ? r4.z : r4.w;
+            sc.pb = 0.0f;
+            sc.sid = (len > 0 && sub < min(a.nkos, len)) ? __ldg(a.pos.indices + sc.ps + lfm_bounded(r, (uint32_t)len)) : 0;
         }
     };
     auto fetch = [&](int base) -> Tuple {
@@ -384,7 +398,7 @@ __global__ void __launch_bounds__(256, MINB) fast_slot_kernel(FitArgs a, const T
 
     int base = warp * NS;  // first tuple of this warp's group; groups are nwarps*NS apart
     Tuple cur = fetch(base < n_tuples ? base : -1);
-    TupleScalars cs = {0.f, 0.f, 0, 0, -1};
+    TupleScalars cs = {0.f, 0.f, 0, 0, -1, 0};
     stage(cur, sbuf, cs);
     cp_async_commit();
     int flip = 0;
@@ -392,24 +406,61 @@ __global__ void __launch_bounds__(256, MINB) fast_slot_kernel(FitArgs a, const T
     for (; base < n_tuples; base += nwarps * NS, flip ^= 1) {
         const int nbase = base + nwarps * NS;
         Tuple nxt = fetch((nbase > 0 && nbase < n_tuples) ? nbase : -1);
-        TupleScalars ns = {0.f, 0.f, 0, 0, -1};
+        TupleScalars ns = {0.f, 0.f, 0, 0, -1, 0};
         float* buf = sbuf + flip * BUFF;
         float* nbuf = sbuf + (flip ^ 1) * BUFF;
         cp_async_wait_all();
         __syncwarp();
-        const bool valid = cur.user >= 0;
+        const bool valid = cur.user >= 0 && (!KOS || cs.pe > cs.ps);  // k-OS skips empty rows (T:972-973)
         const int t = base + slot;
         float4 u[VPL];
+        float4 pk = make_float4(0.f, 0.f, 0.f, 0.f);  // k-OS: the chosen positive's row (not staged)
         float pp = 0.0f;
 #pragma unroll
         for (int v = 0; v < VPL; v++) {
             u[v] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (valid) {
                 u[v] = *(const float4*)(buf + 0 * D + (sub + LPR * v) * 4);
-                pp += dot4(u[v], *(const float4*)(buf + 1 * D + (sub + LPR * v) * 4));
+                if (!KOS) pp += dot4(u[v], *(const float4*)(buf + 1 * D + (sub + LPR * v) * 4));
             }
         }
-        pp = slot_sum<LPR>(pp) + cs.ub + cs.pb;
+        int pos_id = cur.item;
+        if constexpr (KOS) {
+            // ---- T:975-1011: score the sampled positives (two rows in flight per round), keep the
+            //      score of sample j on lane j, take the k-th best in stable descending order ----
+            const int no_pos = valid ? min(a.nkos, cs.pe - cs.ps) : 0;
+            const int slot0 = slot * LPR;
+            float my_val = 0.0f;
+            int maxn = no_pos;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) maxn = max(maxn, __shfl_xor_sync(LFM_FULL, maxn, o));
+            for (int j = 0; j < maxn; j += 2) {
+                const int sa = __shfl_sync(LFM_FULL, cs.sid, slot0 + min(j, LPR - 1));
+                const int sb = __shfl_sync(LFM_FULL, cs.sid, slot0 + min(j + 1, LPR - 1));
+                const bool aa = j < no_pos, ab = j + 1 < no_pos;
+                float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
+                float ba = 0.0f, bb = 0.0f;
+                if (aa) { ra = ldcg4(m.item.w + (size_t)sa * D + sub * 4); ba = __ldcg(m.item.b + sa); }
+                if (ab) { rb = ldcg4(m.item.w + (size_t)sb * D + sub * 4); bb = __ldcg(m.item.b + sb); }
+                const float va = slot_sum<LPR>(dot4(u[0], ra)) + cs.ub + ba;
+                const float vb = slot_sum<LPR>(dot4(u[0], rb)) + cs.ub + bb;
+                if (sub == j) my_val = va;
+                if (sub == j + 1) my_val = vb;
+            }
+            int rank = 0;
+            for (int j = 0; j < maxn; j++) {
+                const float vj = __shfl_sync(LFM_FULL, my_val, slot0 + min(j, LPR - 1));
+                rank += (j < no_pos && (vj > my_val || (vj == my_val && j < sub))) ? 1 : 0;
+            }
+            const int sel = min(a.k, no_pos) - 1;
+            const unsigned hit = __ballot_sync(LFM_FULL, valid && sub < no_pos && rank == sel) & slotmask;
+            const int src = hit ? __ffs(hit) - 1 : slot0;  // NaN scores: fall back to the first sample
+            pos_id = __shfl_sync(LFM_FULL, cs.sid, src);
+            pp = __shfl_sync(LFM_FULL, my_val, src);
+            if (valid) pk = ldcg4(m.item.w + (size_t)pos_id * D + sub * 4);  // T:1005-1011
+        } else {
+            pp = slot_sum<LPR>(pp) + cs.ub + cs.pb;
+        }
 
         int sampled = 0, neg_id = -1;
         float loss = 0.0f;
@@ -417,7 +468,7 @@ __global__ void __launch_bounds__(256, MINB) fast_slot_kernel(FitArgs a, const T
 #pragma unroll
         for (int v = 0; v < VPL; v++) q[v] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-        if constexpr (LOSS == LOSS_WARP) {
+        if constexpr (LOSS == LOSS_WARP || KOS) {
             // ---- rank sampling (T:855-899): every slot draws its own candidates in lockstep ----
             Philox4 r4 = {0u, 0u, 0u, 0u};
             bool active = valid && max_sampled > 0;
@@ -446,7 +497,8 @@ __global__ void __launch_bounds__(256, MINB) fast_slot_kernel(FitArgs a, const T
                             if (sub == 0) c_rej++;
                         } else {
                             neg_id = cand;
-                            loss = fminf(cur.weight * (float)a.loss_table[sampled], (float)LFM_MAX_LOSS);
+                            // T:881 (weight * log term) / T:1039 (k-OS: no weight)
+                            loss = fminf((KOS ? 1.0f : cur.weight) * (float)a.loss_table[sampled], (float)LFM_MAX_LOSS);
                         }
                     }
                     active = neg_id < 0 && sampled < max_sampled;
@@ -494,9 +546,10 @@ __global__ void __launch_bounds__(256, MINB) fast_slot_kernel(FitArgs a, const T
         cp_async_commit();
 
         // ---- update (T:454-534 / T:537-649): rows + biases of a slot, one instruction stream ----
-        const bool upd = LOSS == LOSS_WARP ? neg_id >= 0 : valid;
+        const bool upd = (LOSS == LOSS_WARP || KOS) ? neg_id >= 0 : valid;
         if (__any_sync(LFM_FULL, upd)) {
             float4 gn[VPL];
+            float4 pk_g = make_float4(1.f, 1.f, 1.f, 1.f);  // k-OS: the chosen positive's accumulator row
             float bgv = 1.0f;  // bias accumulator: sub 0 item (positive), 1 negative / user, 2 user
             if (upd) {         // the only fetches left on the critical path, all issued together
                 if constexpr (PAIRWISE) {
@@ -504,20 +557,21 @@ __global__ void __launch_bounds__(256, MINB) fast_slot_kernel(FitArgs a, const T
 #pragma unroll
                     for (int v = 0; v < VPL; v++) gn[v] = ldcg4(m.item.g + on + (sub + LPR * v) * 4);
                     if (sub < 3)
-                        bgv = __ldcg(sub == 0 ? m.item.bg + cur.item : sub == 1 ? m.item.bg + neg_id
-                                                                                 : m.user.bg + cur.user);
+                        bgv = __ldcg(sub == 0 ? m.item.bg + pos_id : sub == 1 ? m.item.bg + neg_id
+                                                                               : m.user.bg + cur.user);
+                    if (KOS) pk_g = ldcg4(m.item.g + (size_t)pos_id * D + sub * 4);
                 } else {
                     if (sub < 2) bgv = __ldcg(sub == 0 ? m.item.bg + cur.item : m.user.bg + cur.user);
                 }
             }
             if (upd) {
-                const size_t op = (size_t)cur.item * D, ou = (size_t)cur.user * D;
+                const size_t op = (size_t)pos_id * D, ou = (size_t)cur.user * D;
 #pragma unroll
                 for (int v = 0; v < VPL; v++) {
                     const int o = (sub + LPR * v) * 4;
-                    const float4 p4 = *(const float4*)(buf + 1 * D + o);
+                    const float4 p4 = KOS ? pk : *(const float4*)(buf + 1 * D + o);
                     const float4 gu = *(const float4*)(buf + 2 * D + o);
-                    const float4 gp = *(const float4*)(buf + 3 * D + o);
+                    const float4 gp = KOS ? pk_g : *(const float4*)(buf + 3 * D + o);
                     const float lx = loss * u[v].x, ly = loss * u[v].y, lz = loss * u[v].z, lw = loss * u[v].w;
                     if constexpr (PAIRWISE) {
                         const size_t on = (size_t)neg_id * D;
@@ -533,8 +587,8 @@ __global__ void __launch_bounds__(256, MINB) fast_slot_kernel(FitArgs a, const T
                 }
                 if constexpr (PAIRWISE) {
                     if (sub < 3) {  // biases: sub 0 positive (-loss), 1 negative (+loss), 2 user (+loss)
-                        float* b = sub == 0 ? m.item.b + cur.item : sub == 1 ? m.item.b + neg_id : m.user.b + cur.user;
-                        float* bg = sub == 0 ? m.item.bg + cur.item : sub == 1 ? m.item.bg + neg_id : m.user.bg + cur.user;
+                        float* b = sub == 0 ? m.item.b + pos_id : sub == 1 ? m.item.b + neg_id : m.user.b + cur.user;
+                        float* bg = sub == 0 ? m.item.bg + pos_id : sub == 1 ? m.item.bg + neg_id : m.user.bg + cur.user;
                         const float g = sub == 0 ? -loss : loss;
                         red_add(b, -lr * rsqrt_ftz(bgv) * g);
                         red_add(bg, g * g);
@@ -628,6 +682,8 @@ cudaError_t launch_fast(const FitArgs& a, const Tuple* tuples, int64_t begin, in
     const Tuple* tp = tuples + begin;
     constexpr int DD = 4 * LPR;
     if constexpr (LOSS == LOSS_KOS) {
+        // slot kernel keeps the n sampled positives one per lane of a slot: needs n <= LPR
+        if (g_tuning != 0 && a.nkos <= LPR) return launch_slot<LOSS, DD, 1, 4>(b, tp, count, st);
         FastGrid g = fast_grid(fast_rank_kernel<LOSS, LPR>, count, lfm_inflight_cap(count));
         fast_rank_kernel<LOSS, LPR><<<g.blocks, g.threads, 0, st>>>(b, tp);
         return cudaGetLastError();

@@ -18,6 +18,8 @@ override with ``LIGHTFM_CUDA_MODE=replay|hogwild|auto`` or :func:`set_mode`.
 import ctypes
 import os
 
+import numpy as np
+
 from . import _abi
 from ._abi import CSRMatrix, FastLightFM  # noqa: F401  (re-exported)
 
@@ -155,6 +157,17 @@ class ResidentPlan(object):
         (loss, item_features, user_features, interactions, user_ids, item_ids, Y, sample_weight,
          lightfm, item_alpha, user_alpha, k, n) = self._args
         self._lightfm = lightfm
+        # same typed-buffer checks as the per-epoch entry points (int32 ids, float32 values)
+        _abi._require(user_ids, np.int32, 1, "user_ids")
+        if item_ids is not None:
+            _abi._require(item_ids, np.int32, 1, "item_ids")
+        if Y is not None:
+            _abi._require(Y, np.float32, 1, "Y")
+        if sample_weight is not None:
+            _abi._require(sample_weight, np.float32, 1, "sample_weight")
+        for name, arr in (("item_ids", item_ids), ("Y", Y), ("sample_weight", sample_weight)):
+            if arr is not None and len(arr) != len(user_ids):
+                raise ValueError("%s has %d entries, expected %d" % (name, len(arr), len(user_ids)))
         n_ex = len(user_ids)
         null_i = ctypes.cast(None, _abi.c_i32p)
         null_f = ctypes.cast(None, _abi.c_f32p)
@@ -167,6 +180,10 @@ class ResidentPlan(object):
             n_ex, lightfm.ptr, float(item_alpha), float(user_alpha), int(k), int(n)))
 
     def epoch(self, seed, num_threads=2, shuffle_indices=None):
+        if shuffle_indices is not None:
+            _abi._require(shuffle_indices, np.int32, 1, "shuffle_indices")
+            if len(shuffle_indices) != len(self._args[4]):
+                raise ValueError("shuffle_indices has the wrong length")
         cnt = _abi.LfmCounters()
         sh = _abi.i32p(shuffle_indices) if shuffle_indices is not None else ctypes.cast(None, _abi.c_i32p)
         _check(_lib.lfm_plan_epoch(self._handle, sh, int(seed) & 0xFFFFFFFF, int(num_threads),

@@ -133,6 +133,25 @@ __device__ __forceinline__ int lfm_bounded(uint32_t r, uint32_t n) {
     return (int)__umulhi(r, n);
 }
 
+// ---- memory helpers --------------------------------------------------------------
+// Fire-and-forget reductions performed in L2 (no return value -> RED, not ATOM).
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c),
+                 "f"(d)
+                 : "memory");
+}
+__device__ __forceinline__ void red_add(float* addr, float a) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
+}
+// L2-coherent vector load (ld.global.cg): tables are updated concurrently by other SMs.
+__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg((const float4*)p); }
+// G >= 1 under adagrad (starts at 1, only grows): no denormals, so the bare approximation is safe
+__device__ __forceinline__ float rsqrt_ftz(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // ---- warp helpers --------------------------------------------------------------
 __device__ __forceinline__ float lfm_warp_sum(float v) {
 #pragma unroll

@@ -19,23 +19,6 @@
 
 namespace {
 
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c),
-                 "f"(d)
-                 : "memory");
-}
-__device__ __forceinline__ void red_add(float* addr, float a) {
-    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
-}
-__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg((const float4*)p); }
-// G >= 1 under adagrad (starts at 1, only grows): no denormals, so the bare approximation is safe
-__device__ __forceinline__ float rsqrt_ftz(float x) {
-    float r;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-
-
 template <int LPR>
 __device__ __forceinline__ float slot_sum(float v) {
 #pragma unroll

@@ -23,7 +23,9 @@ def _fit(api, loss, train, d, epochs, seed, num_threads, schedule="adagrad", **h
 
 
 @pytest.mark.parametrize("loss,d", [("warp", 64), ("bpr", 16), ("logistic", 32), ("warp-kos", 64),
-                                    ("warp", 10)])
+                                    ("warp", 10),        # generic kernel, scalar lanes
+                                    ("warp", 24),        # generic kernel, float4 lanes
+                                    ("warp-kos", 32)])   # n=10 > 8 lanes per slot: first-generation kernel
 def test_hogwild_statistical_parity_with_oracle(loss, d):
     cu, orc = H.cuda_native(), H.oracle_native()
     full = H.planted_interactions(400, 300, 30, seed=5)
@@ -137,6 +139,26 @@ def test_hogwild_with_features_and_l2_learns():
     train, test = H.split(full, 1)
     itf = H.tag_features(200, 20, 3, 5)
     hp = H.Hyper(d=32, item_alpha=1e-5, user_alpha=1e-5)
+    res = []
+    for api, nt in ((orc, 1), (cu, 8)):
+        rs = np.random.RandomState(0)
+        arr = H.init_arrays(rs, itf.shape[1], 300, 32)
+        for _ in range(8):
+            H.run_epoch(api, "warp", train, arr, hp, rs, item_features=itf, num_threads=nt)
+        item_repr = {"item_embeddings": itf @ arr["item_embeddings"], "item_biases": itf @ arr["item_biases"],
+                     "user_embeddings": arr["user_embeddings"], "user_biases": arr["user_biases"]}
+        res.append(H.eval_arrays(item_repr, 32, train, test))
+    assert res[0][1] > 0.65 and res[1][1] > 0.65, res
+    assert abs(res[0][1] - res[1][1]) < 0.03, res
+
+
+def test_hogwild_with_features_no_l2_learns():
+    """Item tag features, adagrad, alpha = 0: BASELINE config 3's path (generic kernel)."""
+    cu, orc = H.cuda_native(), H.oracle_native()
+    full = H.planted_interactions(300, 200, 25, seed=2)
+    train, test = H.split(full, 1)
+    itf = H.tag_features(200, 20, 3, 5)
+    hp = H.Hyper(d=32)
     res = []
     for api, nt in ((orc, 1), (cu, 8)):
         rs = np.random.RandomState(0)

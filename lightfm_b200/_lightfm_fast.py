@@ -101,7 +101,7 @@ _TUNING_NAMES = {0: "fast_rank_kernel<WARP,LPR=d/4>", 4: "fast_slot_kernel<WARP,
 def warp_kernel_name(d=64):
     """Name of the WARP fast-path kernel the current tuning launches (for reports)."""
     t = set_tuning(-1)  # out-of-range: returns the current value without changing it
-    return _TUNING_NAMES.get(t, "?").replace("<d,", "<%d," % d).replace("LPR", str(d // 4))
+    return _TUNING_NAMES.get(t, "?").replace(",d,", ",%d," % d).replace("LPR=d/4", "LPR=%d" % (d // 4))
 
 
 def release_cache():

@@ -119,6 +119,9 @@ int lfm_set_device(int device);
 /* Override the num_threads -> mode mapping (LFM_MODE_AUTO restores it). */
 int lfm_set_mode(int mode);
 int lfm_get_mode(void);
+/* Resident plans answer in_positives (T:270-284) from an exact users x items bitmap when it
+ * fits in `bytes` of HBM (default 1 GiB; 0 disables it: sorted-row search everywhere). */
+int lfm_set_bitmap_limit(int64_t bytes);
 /* Free the cached device staging buffers held by the host entry points. */
 int lfm_release_cache(void);
 

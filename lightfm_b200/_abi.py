@@ -100,6 +100,7 @@ LIB_ONLY = {
     "lfm_set_device": (C.c_int, [C.c_int]),
     "lfm_set_mode": (C.c_int, [C.c_int]),
     "lfm_get_mode": (C.c_int, []),
+    "lfm_set_bitmap_limit": (C.c_int, [C.c_int64]),
     "lfm_release_cache": (C.c_int, []),
     "lfm_plan_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, CsrP, CsrP, CsrP, c_i32p, c_i32p,
                                   c_f32p, c_f32p, C.c_int64, ModelP, C.c_double, C.c_double,

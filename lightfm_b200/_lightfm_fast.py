@@ -104,12 +104,23 @@ def warp_kernel_name(d=64):
     return _TUNING_NAMES.get(t, "?").replace(",d,", ",%d," % d).replace("LPR=d/4", "LPR=%d" % (d // 4))
 
 
+def set_bitmap_limit(nbytes):
+    """Resident plans build an exact users x items membership bitmap of the positives when it
+    fits in `nbytes` (default 1 GiB; 0 disables it and every kernel uses the sorted-row search)."""
+    fn = _lib.lfm_set_bitmap_limit
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_int64]
+    return fn(int(nbytes))
+
+
 def release_cache():
     _check(_lib.lfm_release_cache())
 
 
 if os.environ.get("LIGHTFM_CUDA_INFLIGHT_DIVISOR"):
     set_inflight_divisor(int(os.environ["LIGHTFM_CUDA_INFLIGHT_DIVISOR"]))
+if os.environ.get("LIGHTFM_CUDA_BITMAP_LIMIT"):
+    set_bitmap_limit(int(os.environ["LIGHTFM_CUDA_BITMAP_LIMIT"]))
 if os.environ.get("LIGHTFM_CUDA_TUNING"):
     set_tuning(int(os.environ["LIGHTFM_CUDA_TUNING"]))
 if os.environ.get("LIGHTFM_CUDA_MODE"):

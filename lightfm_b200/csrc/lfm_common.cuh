@@ -75,6 +75,11 @@ struct FitArgs {
     const double* loss_table;      // [max_sampled + 1] log terms precomputed on the host
     DevCounters* counters;
     DevScales* scales;
+    // Optional exact membership bitmap of the positives CSR: bit (u, i) at
+    // pos_bitmap[u * bitmap_words + (i >> 5)] >> (i & 31).  Built once per resident plan when
+    // it fits (lfm_launch_build_bitmap); the kernels fall back to the sorted-row search when null.
+    const uint32_t* pos_bitmap;
+    int32_t bitmap_words;
 };
 
 // ---- launchers (defined in the .cu files) ------------------------------------
@@ -93,6 +98,7 @@ cudaError_t lfm_launch_auc(const DevCsr& ranks, const int32_t* num_train_pos, fl
 cudaError_t lfm_launch_in_positives(const DevCsr& mat, int32_t row, int32_t col, int32_t* out,
                                     cudaStream_t st);
 cudaError_t lfm_launch_check_identity(const DevCsr& m, int32_t* flag, cudaStream_t st);
+cudaError_t lfm_launch_build_bitmap(const DevCsr& pos, uint32_t* bitmap, int32_t words_per_row, cudaStream_t st);
 size_t lfm_item_repr_scratch_floats(const DevCsr& itf, const DevModel& m);
 
 #ifdef __CUDACC__

@@ -65,6 +65,21 @@ __global__ void pack_kernel(const int32_t* __restrict__ user_ids, const int32_t*
     }
 }
 
+// One thread per stored entry of the positives CSR: set its bit (row found by binary search in indptr).
+__global__ void build_bitmap_kernel(DevCsr pos, uint32_t* bitmap, int words) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; e < pos.nnz; e += stride) {
+        int lo = 0, hi = pos.rows;  // largest row with indptr[row] <= e
+        while (hi - lo > 1) {
+            int mid = lo + ((hi - lo) >> 1);
+            if ((int64_t)__ldg(pos.indptr + mid) <= e) lo = mid; else hi = mid;
+        }
+        int item = __ldg(pos.indices + e);
+        atomicOr(bitmap + (size_t)lo * words + (item >> 5), 1u << (item & 31));
+    }
+}
+
 // ---- generic kernel ------------------------------------------------------------
 template <int KPL>
 struct Repr {
@@ -463,6 +478,15 @@ cudaError_t launch_generic_kpl(const FitArgs& a, const Tuple* tuples, int64_t be
 }  // namespace
 
 #include "lfm_hogwild_fast.cuh"
+
+cudaError_t lfm_launch_build_bitmap(const DevCsr& pos, uint32_t* bitmap, int32_t words_per_row, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(bitmap, 0, sizeof(uint32_t) * (size_t)pos.rows * words_per_row, st);
+    if (e != cudaSuccess || pos.nnz == 0) return e;
+    int64_t blocks = (pos.nnz + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    build_bitmap_kernel<<<(int)blocks, 256, 0, st>>>(pos, bitmap, words_per_row);
+    return cudaGetLastError();
+}
 
 // Host-visible helper: is (loss, model, features) eligible for the hogwild path at all?
 extern "C" int lfm_hogwild_supported(int loss, int d, int nkos) {

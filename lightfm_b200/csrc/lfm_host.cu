@@ -23,6 +23,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 int g_mode = LFM_MODE_AUTO;
+int64_t g_bitmap_limit_bytes = (int64_t)1 << 30;  // resident plans: membership bitmap if <= 1 GiB
 int g_device = 0;
 std::mutex g_mu;  // the staging arena is process-global; host entry points serialise on it
 
@@ -483,6 +484,11 @@ extern "C" int lfm_set_mode(int mode) {
     return LFM_OK;
 }
 extern "C" int lfm_get_mode(void) { return g_mode; }
+// Size limit of the positives bitmap a resident plan may build (0 disables it; default 1 GiB).
+extern "C" int lfm_set_bitmap_limit(int64_t bytes) {
+    g_bitmap_limit_bytes = bytes < 0 ? 0 : bytes;
+    return LFM_OK;
+}
 extern "C" int lfm_release_cache(void) {
     std::lock_guard<std::mutex> lock(g_mu);
     for (auto& kv : g_arena)
@@ -711,6 +717,23 @@ extern "C" int lfm_plan_create(lfm_plan** out, int32_t loss, const lfm_csr* item
                     nullptr, no_examples, const_cast<lfm_model*>(model), item_alpha, user_alpha, k, n,
                     2, nullptr, 0};
     rc = stage_fit(loss, in, false, &p->st);
+    if (rc == LFM_OK && loss != LOSS_LOGISTIC && g_bitmap_limit_bytes > 0) {
+        // exact membership bitmap of the positives (users x items bits) when it is small enough:
+        // replaces the sorted-row search (several L2 sectors per violating negative) by one load
+        const DevCsr& pos = p->st.a.pos;
+        const int64_t words = ((int64_t)pos.cols + 31) / 32;
+        const int64_t bytes = words * 4 * (int64_t)pos.rows;
+        if (pos.rows > 0 && words > 0 && bytes <= g_bitmap_limit_bytes) {
+            void* bm = nullptr;
+            rc = arena_get("pos.bitmap", (size_t)bytes, &bm);
+            if (rc == LFM_OK) {
+                cudaError_t e = lfm_launch_build_bitmap(pos, (uint32_t*)bm, (int32_t)words, g_stream);
+                if (e != cudaSuccess) rc = fail(LFM_ERR_CUDA, "bitmap build failed: %s", cudaGetErrorString(e));
+                p->st.a.pos_bitmap = (const uint32_t*)bm;
+                p->st.a.bitmap_words = (int32_t)words;
+            }
+        }
+    }
     if (rc == LFM_OK) {
         cudaError_t e = cudaStreamSynchronize(g_stream);
         if (e != cudaSuccess) rc = fail(LFM_ERR_CUDA, "plan upload failed: %s", cudaGetErrorString(e));

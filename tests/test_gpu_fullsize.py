@@ -129,3 +129,36 @@ def test_host_entry_point_full_size_roundtrip(c2):
     state_bytes = 4 * ((N_ITEMS + N_USERS) * 65 * 2)
     assert c["d2h_bytes"] == state_bytes
     assert c["h2d_bytes"] >= state_bytes + 4 * NNZ * 4 + 4 * NNZ
+
+
+def test_membership_bitmap_and_sorted_row_search_agree(c2):
+    """Resident plans answer in_positives from an exact users x items bitmap when it fits; with the
+    limit at 0 the kernels search the sorted CSR row instead.  Same data, same seeds: the rejection
+    / sampling / update statistics of one epoch must coincide (hogwild => statistically)."""
+    from lightfm_b200 import _lightfm_fast as fast
+    rows, cols = c2
+    y = np.ones(NNZ, np.float32)
+    pos = sp.csr_matrix((y, (rows, cols)), shape=(N_USERS, N_ITEMS))
+    pos.sort_indices()
+    itf = sp.identity(N_ITEMS, dtype=np.float32, format="csr")
+    usf = sp.identity(N_USERS, dtype=np.float32, format="csr")
+    out = []
+    for limit in (1 << 30, 0):
+        fast.set_bitmap_limit(limit)
+        try:
+            st = _state(64)
+            holder = fast.FastLightFM(*st, 64, 0, 0.05, 0.95, 1e-6, 10)
+            plan = fast.ResidentPlan("warp", fast.CSRMatrix(itf), fast.CSRMatrix(usf), fast.CSRMatrix(pos),
+                                     rows, cols, y, y, holder, 0.0, 0.0)
+            c = plan.epoch(seed=11, num_threads=8)
+            plan.close()
+        finally:
+            fast.set_bitmap_limit(1 << 30)
+        out.append(c)
+    a, b = out
+    assert a["positives"] == b["positives"] == NNZ
+    assert a["rejected"] > 0 and abs(a["rejected"] - b["rejected"]) < 0.03 * b["rejected"], (a["rejected"], b["rejected"])
+    # same sampler, but the two kernels run at different speeds, so the concurrently evolving
+    # model differs a little within the epoch: allow 3 %
+    assert abs(a["negatives_drawn"] - b["negatives_drawn"]) < 0.03 * b["negatives_drawn"]
+    assert abs(a["updates"] - b["updates"]) < 0.03 * b["updates"]

@@ -80,6 +80,9 @@ struct FitArgs {
     // it fits (lfm_launch_build_bitmap); the kernels fall back to the sorted-row search when null.
     const uint32_t* pos_bitmap;
     int32_t bitmap_words;
+    // 1 when every Y and every sample weight equals 1.0f (checked on the device when the inputs
+    // are staged): pack_kernel then skips two of its three random reads per interaction.
+    int32_t unit_weights;
 };
 
 // ---- launchers (defined in the .cu files) ------------------------------------
@@ -98,6 +101,7 @@ cudaError_t lfm_launch_auc(const DevCsr& ranks, const int32_t* num_train_pos, fl
 cudaError_t lfm_launch_in_positives(const DevCsr& mat, int32_t row, int32_t col, int32_t* out,
                                     cudaStream_t st);
 cudaError_t lfm_launch_check_identity(const DevCsr& m, int32_t* flag, cudaStream_t st);
+cudaError_t lfm_launch_check_unit(const float* y, const float* w, int64_t n, int32_t* flag, cudaStream_t st);
 cudaError_t lfm_launch_build_bitmap(const DevCsr& pos, uint32_t* bitmap, int32_t words_per_row, cudaStream_t st);
 size_t lfm_item_repr_scratch_floats(const DevCsr& itf, const DevModel& m);
 

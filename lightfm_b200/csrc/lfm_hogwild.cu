@@ -50,7 +50,7 @@ __device__ __forceinline__ int64_t feistel_perm(int64_t i, int64_t n, int hb, ui
 __global__ void pack_kernel(const int32_t* __restrict__ user_ids, const int32_t* __restrict__ item_ids,
                             const float* __restrict__ y, const float* __restrict__ w,
                             const int32_t* __restrict__ shuffle, int64_t n, int hb, uint32_t key,
-                            int skip_nonpositive, Tuple* __restrict__ out) {
+                            int skip_nonpositive, int unit_weights, Tuple* __restrict__ out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
@@ -58,11 +58,20 @@ __global__ void pack_kernel(const int32_t* __restrict__ user_ids, const int32_t*
         Tuple t;
         t.user = user_ids[row];
         t.item = item_ids ? item_ids[row] : (int32_t)i;  // k-OS: the tuple's index in the epoch
-        t.y = y ? y[row] : 1.0f;
-        t.weight = w ? w[row] : 1.0f;
+        t.y = (y && !unit_weights) ? y[row] : 1.0f;
+        t.weight = (w && !unit_weights) ? w[row] : 1.0f;
         if (skip_nonpositive && !(t.y > 0)) t.user = -1;
         out[i] = t;
     }
+}
+
+__global__ void check_unit_kernel(const float* __restrict__ y, const float* __restrict__ w, int64_t n,
+                                  int32_t* flag) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    bool bad = false;
+    for (; i < n; i += stride) bad |= (y[i] != 1.0f) || (w != y && w[i] != 1.0f);
+    if (bad) *flag = 0;
 }
 
 // One thread per stored entry of the positives CSR: set its bit (row found by binary search in indptr).
@@ -479,6 +488,14 @@ cudaError_t launch_generic_kpl(const FitArgs& a, const Tuple* tuples, int64_t be
 
 #include "lfm_hogwild_fast.cuh"
 
+cudaError_t lfm_launch_check_unit(const float* y, const float* w, int64_t n, int32_t* flag, cudaStream_t st) {
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    check_unit_kernel<<<(int)blocks, 256, 0, st>>>(y, w, n, flag);
+    return cudaGetLastError();
+}
+
 cudaError_t lfm_launch_build_bitmap(const DevCsr& pos, uint32_t* bitmap, int32_t words_per_row, cudaStream_t st) {
     cudaError_t e = cudaMemsetAsync(bitmap, 0, sizeof(uint32_t) * (size_t)pos.rows * words_per_row, st);
     if (e != cudaSuccess || pos.nnz == 0) return e;
@@ -508,7 +525,7 @@ cudaError_t lfm_launch_pack(const FitArgs& a, int loss, Tuple* tuples, uint32_t 
     pack_kernel<<<(int)blocks, 256, 0, st>>>(a.user_ids, loss == LOSS_KOS ? nullptr : a.item_ids,
                                              loss == LOSS_KOS ? nullptr : a.y,
                                              loss == LOSS_KOS ? nullptr : a.sample_weight, a.shuffle,
-                                             a.n, hb, perm_key, skip, tuples);
+                                             a.n, hb, perm_key, skip, a.unit_weights, tuples);
     return cudaGetLastError();
 }
 

@@ -327,6 +327,18 @@ int stage_fit(int loss, const FitInputs& in, bool with_shuffle, Staged* out) {
             if (rc != LFM_OK) return rc;
         }
     }
+    if (loss != LOSS_KOS && in.n > 0) {
+        // all-ones Y / weights (the common implicit-feedback case): let pack_kernel skip reading them
+        void* f = nullptr;
+        rc = arena_get("fit.unitflag", sizeof(int32_t), &f);
+        if (rc != LFM_OK) return rc;
+        int32_t one = 1, hflag = 0;
+        CU(cudaMemcpyAsync(f, &one, sizeof(one), cudaMemcpyHostToDevice, g_stream));
+        CU(lfm_launch_check_unit(d_y, d_w, in.n, (int32_t*)f, g_stream));
+        CU(cudaMemcpyAsync(&hflag, f, sizeof(hflag), cudaMemcpyDeviceToHost, g_stream));
+        CU(cudaStreamSynchronize(g_stream));
+        a.unit_weights = hflag;
+    }
     a.user_ids = d_users;
     a.item_ids = d_items;
     a.y = d_y;

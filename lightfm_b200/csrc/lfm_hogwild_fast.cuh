@@ -317,30 +317,8 @@ __device__ __forceinline__ int slot_probe_index(int lo, int hi, int sub) {
     return lo + (int)(((unsigned long long)(unsigned)len * (unsigned)sub) >> LOG);
 }
 
-// L2 eviction-priority hints (createpolicy + .L2::cache_hint): the embedding tables (85 MB at C2)
-// fit the 126 MB L2 but compete with two streams that are read once per epoch -- the packed
-// tuples (320 MB) and the positives-CSR probes (80 MB, random).  Marking those evict_first keeps
-// more table rows resident.
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-    uint64_t pol;
-    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ int4 ldg_stream16(const void* p, uint64_t pol) {
-    int4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ int ldg_stream4(const int* p, uint64_t pol) {
-    int v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
-    return v;
-}
-
-template <int LOSS, int D, int VPL, int MINB, int BT = 256, bool HINTS = false, bool BITMAP = false>
-__global__ void __launch_bounds__(BT, MINB) fast_slot_kernel(FitArgs a, const Tuple* __restrict__ tuples) {
+template <int LOSS, int D, int VPL, int MINB, bool BITMAP = false>
+__global__ void __launch_bounds__(256, MINB) fast_slot_kernel(FitArgs a, const Tuple* __restrict__ tuples) {
     constexpr bool PAIRWISE = LOSS != LOSS_LOGISTIC;  // has a negative item and a positives CSR
     constexpr bool KOS = LOSS == LOSS_KOS;            // positive item chosen in-kernel (T:975-1011)
     static_assert(!KOS || VPL == 1, "k-OS keeps its sampled positives one per lane: VPL must be 1");
@@ -360,8 +338,6 @@ __global__ void __launch_bounds__(BT, MINB) fast_slot_kernel(FitArgs a, const Tu
     const int n_items = a.itf.rows;
     const int max_sampled = m.max_sampled;
     unsigned c_pos = 0, c_neg = 0, c_upd = 0, c_rej = 0;  // per slot, kept on its sub == 0 lane
-    uint64_t pol_stream = 0;
-    if (HINTS) pol_stream = l2_policy_evict_first();
 
     // lane's chunk v of a row starts at float offset (sub + LPR*v)*4: consecutive lanes read
     // consecutive 16 B, so every load instruction of a slot is one contiguous LPR*16 B piece
@@ -384,8 +360,7 @@ __global__ void __launch_bounds__(BT, MINB) fast_slot_kernel(FitArgs a, const Tu
             sc.pe = __ldg(a.pos.indptr + tp.user + 1);
             if (!BITMAP) {
                 const int pi = slot_probe_index<LPR>(sc.ps, sc.pe, sub);
-                if (HINTS) sc.probe = pi >= 0 ? ldg_stream4(a.pos.indices + pi, pol_stream) : -1;
-                else sc.probe = pi >= 0 ? __ldg(a.pos.indices + pi) : -1;
+                sc.probe = pi >= 0 ? __ldg(a.pos.indices + pi) : -1;
             }
         }
         if (KOS) {
@@ -402,14 +377,7 @@ __global__ void __launch_bounds__(BT, MINB) fast_slot_kernel(FitArgs a, const Tu
     auto fetch = [&](int base) -> Tuple {
         Tuple tp = {-1, 0, 0.0f, 0.0f};
         const int t = base + slot;
-        if (base >= 0 && t < n_tuples) {
-            if (HINTS) {
-                const int4 raw = ldg_stream16(tuples + t, pol_stream);
-                tp.user = raw.x; tp.item = raw.y; tp.weight = __int_as_float(raw.z); tp.y = __int_as_float(raw.w);
-            } else {
-                tp = tuples[t];
-            }
-        }
+        if (base >= 0 && t < n_tuples) tp = tuples[t];
         return tp;
     };
 
@@ -671,13 +639,13 @@ FastGrid fast_grid(K kernel, int64_t warps_wanted, int64_t warps_cap) {
     return g;
 }
 
-template <int LOSS, int D, int VPL, int MINB, int BT = 256, bool HINTS = false, bool BITMAP = false>
+template <int LOSS, int D, int VPL, int MINB, bool BITMAP>
 cudaError_t launch_slot_impl(const FitArgs& b, const Tuple* tp, int64_t count, cudaStream_t st) {
     constexpr int LPR = D / (4 * VPL);
     constexpr int NS = 32 / LPR;
-    constexpr int WPB = BT / 32;  // warps per block
+    constexpr int BT = 256, WPB = BT / 32;  // threads / warps per block
     const size_t smem = (size_t)WPB * NS * 2 * 4 * D * sizeof(float);
-    auto kern = fast_slot_kernel<LOSS, D, VPL, MINB, BT, HINTS, BITMAP>;
+    auto kern = fast_slot_kernel<LOSS, D, VPL, MINB, BITMAP>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BT, smem);
@@ -695,12 +663,12 @@ cudaError_t launch_slot_impl(const FitArgs& b, const Tuple* tp, int64_t count, c
     return cudaGetLastError();
 }
 
-template <int LOSS, int D, int VPL, int MINB, int BT = 256, bool HINTS = false>
+template <int LOSS, int D, int VPL, int MINB>
 cudaError_t launch_slot(const FitArgs& b, const Tuple* tp, int64_t count, cudaStream_t st) {
     if constexpr (LOSS != LOSS_LOGISTIC) {
-        if (b.pos_bitmap) return launch_slot_impl<LOSS, D, VPL, MINB, BT, HINTS, true>(b, tp, count, st);
+        if (b.pos_bitmap) return launch_slot_impl<LOSS, D, VPL, MINB, true>(b, tp, count, st);
     }
-    return launch_slot_impl<LOSS, D, VPL, MINB, BT, HINTS, false>(b, tp, count, st);
+    return launch_slot_impl<LOSS, D, VPL, MINB, false>(b, tp, count, st);
 }
 
 // Kernel variant (lfm_set_tuning), measured on C2 in profiles/README.md:
@@ -708,6 +676,9 @@ cudaError_t launch_slot(const FitArgs& b, const Tuple* tp, int64_t count, cudaSt
 //   4 / 5  fast_slot_kernel, one float4 per lane, 3 / 4 CTAs per SM
 //   6/7/8  fast_slot_kernel, two float4 per lane (twice the interactions per warp; d >= 32),
 //          2 / 3 / 4 CTAs per SM                                   [7 = default, fastest on C2]
+// Also tried and dropped (within +-1.5 % of variant 7 once the bitmap was in): 128-thread blocks
+// at 6-8 CTAs per SM (up to 28 warps / SM), and L2 evict-first cache hints on the tuple stream
+// and the CSR probes.
 static int g_tuning = 7;
 
 template <int LOSS, int LPR>
@@ -739,13 +710,6 @@ cudaError_t launch_fast(const FitArgs& a, const Tuple* tuples, int64_t begin, in
         if (g_tuning == 4) return launch_slot<LOSS, DD, 1, 3>(b, tp, count, st);
         if (g_tuning == 5 || g_tuning == 0) return launch_slot<LOSS, DD, 1, 4>(b, tp, count, st);
         if constexpr (DD >= 32) {
-            if constexpr (LOSS == LOSS_WARP && DD == 64) {  // experiments on the headline shape
-                if (g_tuning == 9) return launch_slot<LOSS, DD, 2, 6, 128>(b, tp, count, st);
-                if (g_tuning == 10) return launch_slot<LOSS, DD, 2, 7, 128>(b, tp, count, st);
-                if (g_tuning == 11) return launch_slot<LOSS, DD, 2, 8, 128>(b, tp, count, st);
-                if (g_tuning == 12) return launch_slot<LOSS, DD, 2, 3, 256, true>(b, tp, count, st);
-                if (g_tuning == 13) return launch_slot<LOSS, DD, 2, 7, 128, true>(b, tp, count, st);
-            }
             if (g_tuning == 6) return launch_slot<LOSS, DD, 2, 2>(b, tp, count, st);
             if (g_tuning == 8) return launch_slot<LOSS, DD, 2, 4>(b, tp, count, st);
             return launch_slot<LOSS, DD, 2, 3>(b, tp, count, st);
@@ -772,7 +736,7 @@ cudaError_t launch_fast_d(const FitArgs& a, const Tuple* tuples, int64_t begin, 
 
 extern "C" int lfm_set_tuning(int variant) {
     int old = g_tuning;
-    if (variant == 0 || (variant >= 4 && variant <= 13)) g_tuning = variant;
+    if (variant == 0 || (variant >= 4 && variant <= 8)) g_tuning = variant;
     return old;
 }
 

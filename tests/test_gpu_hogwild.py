@@ -194,3 +194,23 @@ def test_midscale_hogwild_matches_oracle_heldout_metrics():
     assert res[0][1] > 0.7 and res[1][1] > 0.7, res
     assert abs(res[0][1] - res[1][1]) < 0.02, res
     assert abs(res[0][0] - res[1][0]) <= 0.12 * res[0][0] + 0.005, res
+
+
+@pytest.mark.parametrize("variant", (0, 4, 5, 6, 7, 8))
+@pytest.mark.parametrize("bitmap", (True, False))
+def test_every_warp_kernel_variant_trains(variant, bitmap):
+    """lfm_set_tuning selects the WARP fast-path kernel; every variant (with and without the
+    membership bitmap) must process each interaction once, apply updates and learn the planted
+    structure as well as the default."""
+    from lightfm_b200 import LightFM, _lightfm_fast as fast
+    full = H.planted_interactions(400, 300, 30, seed=5)
+    train, test = H.split(full, 7)
+    old = fast.set_tuning(variant)
+    fast.set_bitmap_limit((1 << 30) if bitmap else 0)
+    try:
+        model = LightFM(loss="warp", no_components=64, random_state=1).fit(train, epochs=8, num_threads=8)
+    finally:
+        fast.set_tuning(old)
+        fast.set_bitmap_limit(1 << 30)
+    _, auc = H.eval_arrays({k: getattr(model, k) for k in H.MODEL_ARRAYS}, 64, train, test)
+    assert auc > 0.8, auc

@@ -63,64 +63,132 @@ __global__ void item_repr_kernel(DevCsr itf, DevModel m, float* repr_t, int n_it
         gather_to(itf, m.item.w, m.item.b, m.d, (int)it, repr_t + it, (size_t)n_items, lane);
 }
 
-// One CTA per user with test interactions (persistent loop).
-//   A: user representation -> shared
-//   B: score every item (thread per item, coalesced over the transposed table) -> scratch row;
-//      train positives are then overwritten with NaN (NaN >= x is false, so they never count)
-//   C: one warp per test item counts items with score >= its score (T:1317-1319)
-__global__ void predict_ranks_kernel(DevCsr usf, DevCsr test, DevCsr train, DevModel m,
-                                     const float* __restrict__ item_repr_t, float* scratch,
-                                     float* ranks) {
+// ---- predict_ranks (T:1232-1323), tiled over users ---------------------------------------
+// rank[t] = #{ items i : i not a train positive of the user, i != t, score(u,i) >= score(u,t) }.
+// A CTA takes UT users with test interactions at a time, so every element of the (transposed)
+// item table it streams is used for UT scores instead of one: scores are accumulated per
+// (user, item) in the reference's order (fp32 multiply then add, components left to right), and
+// are compared with the users' test scores as soon as they exist -- nothing is written back.
+// Train positives are handled by subtraction: count over ALL items, then take away the train
+// positives' contribution (the same comparison on the same recomputed scores), which equals
+// skipping them (T:1303-1304).  Comparisons with NaN are false in both passes, as in the reference.
+#define RANK_UT 8    // users per tile (= warps per CTA)
+#define RANK_TCH 64  // test interactions per user handled per pass over the catalogue
+
+__global__ void compact_users_kernel(DevCsr test, int32_t* list, int32_t* count) {
+    int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < test.rows && test.indptr[u + 1] > test.indptr[u]) list[atomicAdd(count, 1)] = u;
+}
+
+__device__ __forceinline__ float rank_score(const float* __restrict__ u, const float* __restrict__ irt,
+                                            int n_items, int d, int item) {
+    float r = u[d] + irt[(size_t)d * n_items + item];
+    for (int j = 0; j < d; j++) r = r + u[j] * irt[(size_t)j * n_items + item];
+    return r;
+}
+
+__global__ void __launch_bounds__(RANK_UT * 32) predict_ranks_tiled_kernel(
+    DevCsr usf, DevCsr test, DevCsr train, DevModel m, const float* __restrict__ irt,
+    const int32_t* __restrict__ active, const int32_t* __restrict__ n_active_p, float* ranks) {
     extern __shared__ float sm[];
-    int d = m.d;
-    int n_items = test.cols;
-    float* u = sm;  // [d+1]
-    float* row = scratch + (size_t)blockIdx.x * n_items;
-    int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    for (int user = blockIdx.x; user < test.rows; user += gridDim.x) {
-        int ts = test.indptr[user], te = test.indptr[user + 1];
-        if (te == ts) continue;
+    const int d = m.d, n_items = test.cols;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float* ur = sm;                                        // [UT][d+1]
+    float* tp = ur + RANK_UT * (d + 1);                    // [UT][TCH] test scores
+    int* tid = (int*)(tp + RANK_UT * RANK_TCH);            // [UT][TCH] test item ids
+    int* cnt = tid + RANK_UT * RANK_TCH;                   // [UT warps][UT][TCH] partial counts
+    int* sub = cnt + RANK_UT * RANK_UT * RANK_TCH;         // [UT][TCH] train-positive counts
+    __shared__ int s_user[RANK_UT], s_ts[RANK_UT], s_T[RANK_UT];
+    const int n_active = *n_active_p;
+
+    for (int tile = blockIdx.x; tile * RANK_UT < n_active; tile += gridDim.x) {
         __syncthreads();
-        if (wib == 0) gather_to(usf, m.user.w, m.user.b, d, user, u, 1, lane);
-        __syncthreads();
-        for (int it = threadIdx.x; it < n_items; it += blockDim.x) {
-            float r = u[d] + item_repr_t[(size_t)d * n_items + it];
-            for (int j = 0; j < d; j++) r = r + u[j] * item_repr_t[(size_t)j * n_items + it];
-            row[it] = r;
+        if (threadIdx.x < RANK_UT) {
+            int k = tile * RANK_UT + threadIdx.x;
+            int u = k < n_active ? active[k] : -1;
+            s_user[threadIdx.x] = u;
+            s_ts[threadIdx.x] = u >= 0 ? test.indptr[u] : 0;
+            s_T[threadIdx.x] = u >= 0 ? test.indptr[u + 1] - test.indptr[u] : 0;
         }
         __syncthreads();
-        int trs = train.indptr[user], tre = train.indptr[user + 1];
-        // Test predictions go to shared memory in chunks of 1024, recomputed from the
-        // transposed table (same arithmetic as phase B), so a test item that is also a train
-        // positive keeps its own score (T:1283-1298) while its row[] slot is masked.
-        for (int base = ts; base < te; base += 1024) {
-            int cnt = min(1024, te - base);
-            float* tp = sm + (d + 1);  // [1024] predictions of this chunk
-            __syncthreads();
-            for (int t = threadIdx.x; t < cnt; t += blockDim.x) {
-                int id = test.indices[base + t];
-                // recompute from the unmasked definition: same arithmetic as above
-                float r = u[d] + item_repr_t[(size_t)d * n_items + id];
-                for (int j = 0; j < d; j++) r = r + u[j] * item_repr_t[(size_t)j * n_items + id];
-                tp[t] = r;
-            }
-            __syncthreads();
-            if (base == ts) {
-                for (int t = trs + threadIdx.x; t < tre; t += blockDim.x) {
-                    int id = train.indices[t];
-                    if (id >= 0 && id < n_items) row[id] = __int_as_float(0x7fc00000);
+        // A: warp w builds user w's representation (zeros for an empty slot)
+        if (s_user[w] >= 0) gather_to(usf, m.user.w, m.user.b, d, s_user[w], ur + w * (d + 1), 1, lane);
+        else for (int j = lane; j <= d; j += 32) ur[w * (d + 1) + j] = 0.0f;
+        int maxT = 0;
+        for (int u = 0; u < RANK_UT; u++) maxT = max(maxT, s_T[u]);
+        __syncthreads();
+
+        for (int c0 = 0; c0 < maxT; c0 += RANK_TCH) {
+            // B0: this chunk's test scores (T:1283-1298) and cleared counters
+            for (int x = threadIdx.x; x < RANK_UT * RANK_TCH; x += blockDim.x) {
+                int u = x / RANK_TCH, t = x % RANK_TCH;
+                if (c0 + t < s_T[u]) {
+                    int id = test.indices[s_ts[u] + c0 + t];
+                    tid[x] = id;
+                    tp[x] = rank_score(ur + u * (d + 1), irt, n_items, d, id);
                 }
-                __syncthreads();
+                sub[x] = 0;
             }
-            for (int t = wib; t < cnt; t += nwarp) {
-                int id = test.indices[base + t];
-                float p = tp[t];
-                int c = 0;
-                for (int it = lane; it < n_items; it += 32) c += (it != id && row[it] >= p) ? 1 : 0;
+            for (int x = threadIdx.x; x < RANK_UT * RANK_UT * RANK_TCH; x += blockDim.x) cnt[x] = 0;
+            __syncthreads();
+
+            // B + C: stream the catalogue once; UT scores per item element read
+            for (int i0 = 0; i0 < n_items; i0 += blockDim.x) {
+                const int i = i0 + threadIdx.x;
+                const bool in = i < n_items;
+                float acc[RANK_UT];
+                {
+                    const float vb = in ? irt[(size_t)d * n_items + i] : 0.0f;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(LFM_FULL, c, o);
-                if (lane == 0) ranks[base + t] += (float)c;
+                    for (int u = 0; u < RANK_UT; u++) acc[u] = ur[u * (d + 1) + d] + vb;
+                }
+                for (int j = 0; j < d; j++) {
+                    const float v = in ? irt[(size_t)j * n_items + i] : 0.0f;
+#pragma unroll
+                    for (int u = 0; u < RANK_UT; u++) acc[u] = acc[u] + ur[u * (d + 1) + j] * v;
+                }
+#pragma unroll
+                for (int u = 0; u < RANK_UT; u++) {
+                    const int Tc = min(RANK_TCH, s_T[u] - c0);
+                    for (int t = 0; t < Tc; t++) {
+                        const bool hit = in && i != tid[u * RANK_TCH + t] && acc[u] >= tp[u * RANK_TCH + t];
+                        const unsigned bal = __ballot_sync(LFM_FULL, hit);
+                        if (lane == 0) cnt[(w * RANK_UT + u) * RANK_TCH + t] += __popc(bal);
+                    }
+                }
             }
+            // D: the train positives' share of those counts (warp w <-> user w)
+            {
+                const int u = s_user[w];
+                const int Tc = min(RANK_TCH, s_T[w] - c0);
+                if (u >= 0 && Tc > 0 && u < train.rows) {
+                    const int rs = train.indptr[u], re = train.indptr[u + 1];
+                    for (int e0 = rs; e0 < re; e0 += 32) {
+                        const int e = e0 + lane;
+                        bool in = e < re;
+                        int item = in ? train.indices[e] : -1;
+                        if (in && e > rs && train.indices[e - 1] == item) in = false;  // duplicate entry
+                        if (in && (item < 0 || item >= n_items)) in = false;
+                        const float sc = in ? rank_score(ur + w * (d + 1), irt, n_items, d, item) : 0.0f;
+                        for (int t = 0; t < Tc; t++) {
+                            const bool hit = in && item != tid[w * RANK_TCH + t] && sc >= tp[w * RANK_TCH + t];
+                            const unsigned bal = __ballot_sync(LFM_FULL, hit);
+                            if (lane == 0) sub[w * RANK_TCH + t] += __popc(bal);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            // E: reduce over warps and accumulate into ranks (pre-zeroed by the caller, L:968-975)
+            for (int x = threadIdx.x; x < RANK_UT * RANK_TCH; x += blockDim.x) {
+                int u = x / RANK_TCH, t = x % RANK_TCH;
+                if (c0 + t < s_T[u]) {
+                    int total = 0;
+                    for (int ww = 0; ww < RANK_UT; ww++) total += cnt[(ww * RANK_UT + u) * RANK_TCH + t];
+                    ranks[s_ts[u] + c0 + t] += (float)(total - sub[x]);
+                }
+            }
+            __syncthreads();
         }
     }
 }
@@ -182,36 +250,35 @@ size_t lfm_item_repr_scratch_floats(const DevCsr& itf, const DevModel& m) {
     return (size_t)itf.rows * (m.d + 1);
 }
 
-static int ranks_grid(const DevCsr& test) {
-    int g = 148 * 2;
-    if (g > test.rows) g = test.rows;
-    return g < 1 ? 1 : g;
-}
-
 cudaError_t lfm_launch_predict_ranks(const DevCsr& itf, const DevCsr& usf, const DevCsr& test,
                                      const DevCsr& train, const DevModel& m, float* ranks,
                                      float* scratch, cudaStream_t st, int* launches) {
-    // scratch layout: [ (d+1) * n_items transposed item table | grid * n_items score rows ]
+    // scratch layout: [ (d+1) * n_items transposed item table | test.rows + 1 ints: active users, count ]
     int n_items = test.cols;
     if (test.rows == 0 || test.nnz == 0 || n_items == 0) return cudaSuccess;
     float* repr_t = scratch;
-    float* rows = scratch + (size_t)n_items * (m.d + 1);
+    int32_t* active = (int32_t*)(scratch + (size_t)n_items * (m.d + 1));
+    int32_t* count = active + test.rows;
     int64_t blocks = ((int64_t)n_items * 32 + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    DevCsr itf_n = itf;
-    item_repr_kernel<<<(int)blocks, 256, 0, st>>>(itf_n, m, repr_t, n_items);
-    size_t smem = (size_t)(m.d + 1 + 1024) * sizeof(float);
-    predict_ranks_kernel<<<ranks_grid(test), 512, smem, st>>>(usf, test, train, m, repr_t, rows, ranks);
-    if (launches) *launches += 2;
+    item_repr_kernel<<<(int)blocks, 256, 0, st>>>(itf, m, repr_t, n_items);
+    cudaError_t e = cudaMemsetAsync(count, 0, sizeof(int32_t), st);
+    if (e != cudaSuccess) return e;
+    compact_users_kernel<<<(test.rows + 255) / 256, 256, 0, st>>>(test, active, count);
+    size_t smem = sizeof(float) * (RANK_UT * (m.d + 1) + RANK_UT * RANK_TCH) +
+                  sizeof(int) * (RANK_UT * RANK_TCH + RANK_UT * RANK_UT * RANK_TCH + RANK_UT * RANK_TCH);
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(predict_ranks_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int grid = (test.rows + RANK_UT - 1) / RANK_UT;
+    if (grid > 148 * 4) grid = 148 * 4;
+    predict_ranks_tiled_kernel<<<grid, RANK_UT * 32, smem, st>>>(usf, test, train, m, repr_t, active, count, ranks);
+    if (launches) *launches += 3;
     return cudaGetLastError();
 }
 
 // exported for the host layer: number of floats predict_ranks needs in `scratch`
 extern "C" size_t lfm_ranks_scratch_floats(int n_items, int d, int test_rows) {
-    int g = 148 * 2;
-    if (g > test_rows) g = test_rows;
-    if (g < 1) g = 1;
-    return (size_t)n_items * (d + 1) + (size_t)g * n_items;
+    return (size_t)n_items * (d + 1) + (size_t)test_rows + 4;
 }
 
 cudaError_t lfm_launch_auc(const DevCsr& ranks, const int32_t* num_train_pos, float* rank_data,

@@ -104,13 +104,18 @@ def warp_kernel_name(d=64):
     return _TUNING_NAMES.get(t, "?").replace(",d,", ",%d," % d).replace("LPR=d/4", "LPR=%d" % (d // 4))
 
 
+_bitmap_limit = [1 << 30]
+
+
+def bitmap_limit():
+    return _bitmap_limit[0]
+
+
 def set_bitmap_limit(nbytes):
     """Resident plans build an exact users x items membership bitmap of the positives when it
     fits in `nbytes` (default 1 GiB; 0 disables it and every kernel uses the sorted-row search)."""
-    fn = _lib.lfm_set_bitmap_limit
-    fn.restype = ctypes.c_int
-    fn.argtypes = [ctypes.c_int64]
-    return fn(int(nbytes))
+    _bitmap_limit[0] = max(0, int(nbytes))
+    return _lib.lfm_set_bitmap_limit(int(nbytes))
 
 
 def release_cache():

@@ -74,6 +74,16 @@ __global__ void check_unit_kernel(const float* __restrict__ y, const float* __re
     if (bad) *flag = 0;
 }
 
+__global__ void build_bitmap_coo_kernel(const int32_t* __restrict__ user_ids, const int32_t* __restrict__ item_ids,
+                                        int64_t n, uint32_t* bitmap, int words) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; e < n; e += stride) {
+        const int item = item_ids[e];
+        atomicOr(bitmap + (size_t)user_ids[e] * words + (item >> 5), 1u << (item & 31));
+    }
+}
+
 // One thread per stored entry of the positives CSR: set its bit (row found by binary search in indptr).
 __global__ void build_bitmap_kernel(DevCsr pos, uint32_t* bitmap, int words) {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -493,6 +503,16 @@ cudaError_t lfm_launch_check_unit(const float* y, const float* w, int64_t n, int
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
     check_unit_kernel<<<(int)blocks, 256, 0, st>>>(y, w, n, flag);
+    return cudaGetLastError();
+}
+
+cudaError_t lfm_launch_build_bitmap_coo(const int32_t* user_ids, const int32_t* item_ids, int64_t n,
+                                        uint32_t* bitmap, int32_t rows, int32_t words_per_row, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(bitmap, 0, sizeof(uint32_t) * (size_t)rows * words_per_row, st);
+    if (e != cudaSuccess || n == 0) return e;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    build_bitmap_coo_kernel<<<(int)blocks, 256, 0, st>>>(user_ids, item_ids, n, bitmap, words_per_row);
     return cudaGetLastError();
 }
 

@@ -696,7 +696,7 @@ cudaError_t launch_fast(const FitArgs& a, const Tuple* tuples, int64_t begin, in
         return cudaGetLastError();
     } else {
         if constexpr (LOSS == LOSS_WARP) {
-            if (g_tuning == 0) {
+            if (g_tuning == 0 && b.pos.indptr != nullptr) {  // the first-generation kernel searches the CSR
                 FastGrid g = fast_grid(fast_rank_kernel<LOSS, LPR>, count, lfm_inflight_cap(count));
                 fast_rank_kernel<LOSS, LPR><<<g.blocks, g.threads, 0, st>>>(b, tp);
                 return cudaGetLastError();
@@ -752,7 +752,8 @@ static cudaError_t lfm_try_launch_fast(int loss, const FitArgs& a, const Tuple* 
                                        int64_t begin, int64_t count, cudaStream_t st, bool* done) {
     *done = false;
     const DevModel& m = a.model;
-    if (!g_fast_enabled) return cudaSuccess;
+    const bool csr_free = loss != LOSS_LOGISTIC && a.pos.indptr == nullptr;  // bitmap-only plan
+    if (!g_fast_enabled && !csr_free) return cudaSuccess;
     if (!a.itf.identity || !a.usf.identity) return cudaSuccess;
     if (m.adadelta || a.item_alpha != 0.0 || a.user_alpha != 0.0) return cudaSuccess;
     if (loss == LOSS_KOS && a.nkos > 32) return cudaSuccess;

@@ -129,3 +129,34 @@ def test_sharded_trainer_single_rank_matches_plain_fit_statistically():
     p2, auc2 = H.eval_arrays({k: getattr(plain, k) for k in H.MODEL_ARRAYS}, 32, train, test)
     assert auc > 0.65 and abs(auc - auc2) < 0.03, (auc, auc2)
     assert np.all(model.item_embedding_gradients >= 1) and np.any(model.user_embedding_gradients > 1)
+
+
+def test_csr_free_resident_fit_learns_and_matches_csr_path():
+    """WARP / BPR with identity features on the bitmap fast path never build the positives CSR on
+    the host (the library builds a membership bitmap from the COO arrays).  The fit must learn the
+    planted structure as well as the CSR-backed path (bitmap disabled -> sorted-row search)."""
+    from lightfm_b200 import _lightfm_fast as fast
+    full = H.planted_interactions(400, 300, 30, seed=5)
+    train, test = H.split(full, 7)
+    res = {}
+    for name, limit in (("bitmap", 1 << 30), ("csr", 0)):
+        fast.set_bitmap_limit(limit)
+        try:
+            for loss, d in (("warp", 64), ("bpr", 16)):
+                m = LightFM(loss=loss, no_components=d, random_state=1).fit(train, epochs=8, num_threads=8)
+                res[(name, loss)] = H.eval_arrays({k: getattr(m, k) for k in H.MODEL_ARRAYS}, d, train, test)[1]
+        finally:
+            fast.set_bitmap_limit(1 << 30)
+    for loss in ("warp", "bpr"):
+        assert res[("bitmap", loss)] > 0.75 and abs(res[("bitmap", loss)] - res[("csr", loss)]) < 0.03, res
+
+
+def test_plan_without_csr_is_refused_off_the_fast_path():
+    from lightfm_b200 import _lightfm_fast as fast
+    inter = H.synthetic_interactions(60, 50, 500, 1)
+    arrays = H.init_arrays(np.random.RandomState(0), 50, 60, 10)   # d = 10: not a fast-path size
+    holder = H.holder(fast, arrays, H.Hyper(d=10))
+    ident = lambda n: fast.CSRMatrix(sp.identity(n, dtype=np.float32, format="csr"))
+    with pytest.raises(ValueError):
+        fast.ResidentPlan("warp", ident(50), ident(60), None, inter.row, inter.col, inter.data, inter.data,
+                          holder, 0.0, 0.0)

@@ -36,6 +36,17 @@ struct ReplayShared {
 __device__ void gather(const DevCsr& f, const float* emb, const float* bias, int d, int row,
                        double scale, float* repr, int lane) {
     __syncwarp();  // previous readers of repr are done
+    if (f.identity) {
+        // identity features: the row has the single entry (row, 1.0f).  Same operations as the
+        // loop below -- fw = f32(double(1.0f) * scale), repr = 0.0f + fw * E -- without the three
+        // dependent CSR loads.
+        const float fw = (float)((double)1.0f * scale);
+        const float* r = emb + (size_t)row * d;
+        for (int j = lane; j < d; j += 32) repr[j] = 0.0f + fw * r[j];
+        if (lane == 0) repr[d] = 0.0f + fw * bias[row];
+        __syncwarp();
+        return;
+    }
     int start = f.indptr[row], stop = f.indptr[row + 1];
     for (int j = lane; j < d; j += 32) repr[j] = 0.0f;
     if (lane == 0) repr[d] = 0.0f;
@@ -47,6 +58,33 @@ __device__ void gather(const DevCsr& f, const float* emb, const float* bias, int
         if (lane == 0) repr[d] = repr[d] + fw * bias[ft];
     }
     __syncwarp();
+}
+
+// Two independent gathers (user + positive item).  With identity features on both sides their
+// row loads are issued together so the two L2 round trips overlap; otherwise one after the other.
+__device__ void gather2(const DevCsr& fa, const float* ea, const float* ba, int rowa, double sa, float* ra,
+                        const DevCsr& fb, const float* eb, const float* bb, int rowb, double sb, float* rb,
+                        int d, int lane) {
+    if (fa.identity && fb.identity) {
+        __syncwarp();
+        const float fwa = (float)((double)1.0f * sa), fwb = (float)((double)1.0f * sb);
+        const float* pa = ea + (size_t)rowa * d;
+        const float* pb = eb + (size_t)rowb * d;
+        for (int j = lane; j < d; j += 32) {
+            const float xa = pa[j], xb = pb[j];
+            ra[j] = 0.0f + fwa * xa;
+            rb[j] = 0.0f + fwb * xb;
+        }
+        if (lane == 0) {
+            const float xa = ba[rowa], xb = bb[rowb];
+            ra[d] = 0.0f + fwa * xa;
+            rb[d] = 0.0f + fwb * xb;
+        }
+        __syncwarp();
+        return;
+    }
+    gather(fa, ea, ba, d, rowa, sa, ra, lane);
+    gather(fb, eb, bb, d, rowb, sb, rb, lane);
 }
 
 // T:320-334: strictly left-to-right fp32 sum; every lane computes the same value.
@@ -87,6 +125,9 @@ __device__ double step(float* theta, float* G, float* M, double fw, double gradi
 __device__ double bias_steps(const DevCsr& f, int row, DevTable& t, double gradient,
                              const DevModel& m, double alpha) {
     double s = 0.0;
+    if (f.identity)  // single entry (row, 1.0f): 0.0 + llr, as the loop below would compute
+        return s + step(&t.b[row], &t.bg[row], t.bm ? &t.bm[row] : nullptr, (double)1.0f, gradient,
+                        m.adadelta, (double)m.lr, alpha, m.rho, m.eps);
     int start = f.indptr[row], stop = f.indptr[row + 1];
     for (int i = start; i < stop; i++) {
         int ft = f.indices[i];
@@ -99,6 +140,11 @@ __device__ double bias_steps(const DevCsr& f, int row, DevTable& t, double gradi
 __device__ double row_steps(const DevCsr& f, int row, DevTable& t, int comp, double gradient,
                             const DevModel& m, double alpha) {
     double s = 0.0;
+    if (f.identity) {
+        size_t o = (size_t)row * m.d + comp;
+        return s + step(&t.w[o], &t.g[o], t.m ? &t.m[o] : nullptr, (double)1.0f, gradient,
+                        m.adadelta, (double)m.lr, alpha, m.rho, m.eps);
+    }
     int start = f.indptr[row], stop = f.indptr[row + 1];
     for (int i = start; i < stop; i++) {
         size_t o = (size_t)f.indices[i] * m.d + comp;
@@ -108,7 +154,7 @@ __device__ double row_steps(const DevCsr& f, int row, DevTable& t, int comp, dou
     return s;
 }
 
-__device__ int nnz_of(const DevCsr& f, int row) { return f.indptr[row + 1] - f.indptr[row]; }
+__device__ int nnz_of(const DevCsr& f, int row) { return f.identity ? 1 : f.indptr[row + 1] - f.indptr[row]; }
 
 // T:537-649.  Returns avg learning rate contribution via scales update.
 __device__ void warp_update(FitArgs& a, double loss, int user, int pos_id, int neg_id,
@@ -116,7 +162,14 @@ __device__ void warp_update(FitArgs& a, double loss, int user, int pos_id, int n
     DevModel& m = a.model;
     int d = m.d;
     double b0 = 0.0, b1 = 0.0, b2 = 0.0;
-    if (lane == 0) {
+    if (a.itf.identity && a.usf.identity && pos_id != neg_id) {
+        // three different addresses: lanes 0 / 1 / 2 take one bias each, round trips overlap
+        if (lane == 0) b0 = bias_steps(a.itf, pos_id, m.item, -loss, m, a.item_alpha);
+        if (lane == 1) b1 = bias_steps(a.itf, neg_id, m.item, loss, m, a.item_alpha);
+        if (lane == 2) b2 = bias_steps(a.usf, user, m.user, loss, m, a.user_alpha);
+        b1 = __shfl_sync(LFM_FULL, b1, 1);
+        b2 = __shfl_sync(LFM_FULL, b2, 2);
+    } else if (lane == 0) {
         b0 = bias_steps(a.itf, pos_id, m.item, -loss, m, a.item_alpha);
         b1 = bias_steps(a.itf, neg_id, m.item, loss, m, a.item_alpha);
         b2 = bias_steps(a.usf, user, m.user, loss, m, a.user_alpha);
@@ -217,8 +270,8 @@ __global__ void __launch_bounds__(32, 1) replay_kernel(FitArgs a) {
         if (LOSS == LOSS_LOGISTIC) {
             int item = a.item_ids[row];
             float weight = a.sample_weight[row];
-            gather(a.usf, m.user.w, m.user.b, d, user, user_scale, sh.u, lane);
-            gather(a.itf, m.item.w, m.item.b, d, item, item_scale, sh.pos, lane);
+            gather2(a.usf, m.user.w, m.user.b, user, user_scale, sh.u,
+                    a.itf, m.item.w, m.item.b, item, item_scale, sh.pos, d, lane);
             double prediction = (double)sigmoid_ref(score(sh.u, sh.pos, d));
             int y = (a.y[row] <= 0) ? 0 : 1;
             double loss = (double)weight * (prediction - (double)y);
@@ -229,8 +282,8 @@ __global__ void __launch_bounds__(32, 1) replay_kernel(FitArgs a) {
             if (!(a.y[row] > 0)) continue;
             float weight = a.sample_weight[row];
             c_pos++;
-            gather(a.usf, m.user.w, m.user.b, d, user, user_scale, sh.u, lane);
-            gather(a.itf, m.item.w, m.item.b, d, pos_id, item_scale, sh.pos, lane);
+            gather2(a.usf, m.user.w, m.user.b, user, user_scale, sh.u,
+                    a.itf, m.item.w, m.item.b, pos_id, item_scale, sh.pos, d, lane);
             double pp = (double)score(sh.u, sh.pos, d);
             int sampled = 0;
             while (sampled < m.max_sampled) {
@@ -240,7 +293,7 @@ __global__ void __launch_bounds__(32, 1) replay_kernel(FitArgs a) {
                 double np = (double)score(sh.u, sh.neg, d);
                 c_neg++;
                 if (np > pp - 1) {
-                    if (lfm_bsearch(a.pos.indices, a.pos.indptr[user], a.pos.indptr[user + 1], neg_id)) {
+                    if (lfm_warp_member(a.pos.indices, a.pos.indptr[user], a.pos.indptr[user + 1], neg_id, lane)) {
                         c_rej++;
                         continue;
                     }
@@ -259,11 +312,11 @@ __global__ void __launch_bounds__(32, 1) replay_kernel(FitArgs a) {
             for (int64_t j = 0; j < a.n; j++) {  // T:1123-1127
                 neg_id = a.item_ids[lfm_rand_r(seed) % (int)a.n];
                 c_neg++;
-                if (!lfm_bsearch(a.pos.indices, a.pos.indptr[user], a.pos.indptr[user + 1], neg_id)) break;
+                if (!lfm_warp_member(a.pos.indices, a.pos.indptr[user], a.pos.indptr[user + 1], neg_id, lane)) break;
                 c_rej++;
             }
-            gather(a.usf, m.user.w, m.user.b, d, user, user_scale, sh.u, lane);
-            gather(a.itf, m.item.w, m.item.b, d, pos_id, item_scale, sh.pos, lane);
+            gather2(a.usf, m.user.w, m.user.b, user, user_scale, sh.u,
+                    a.itf, m.item.w, m.item.b, pos_id, item_scale, sh.pos, d, lane);
             gather(a.itf, m.item.w, m.item.b, d, neg_id, item_scale, sh.neg, lane);
             double pp = (double)score(sh.u, sh.pos, d);
             double np = (double)score(sh.u, sh.neg, d);
@@ -307,7 +360,7 @@ __global__ void __launch_bounds__(32, 1) replay_kernel(FitArgs a) {
                 double np = (double)score(sh.u, sh.neg, d);
                 c_neg++;
                 if (np > pp - 1) {
-                    if (lfm_bsearch(a.pos.indices, ps, pe, neg_id)) { c_rej++; continue; }
+                    if (lfm_warp_member(a.pos.indices, ps, pe, neg_id, lane)) { c_rej++; continue; }
                     double loss = a.loss_table[sampled];  // T:1039: no weight, no max(1, .)
                     if (loss > LFM_MAX_LOSS) loss = LFM_MAX_LOSS;
                     warp_update(a, loss, user, pos_id, neg_id, sh, item_scale, user_scale, lane);

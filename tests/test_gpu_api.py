@@ -56,13 +56,23 @@ def test_return_self_and_feature_shape_errors():  # tests/test_api.py:121-168
 
 
 def test_overflow_divergence_raises():  # tests/test_api.py:285-294
+    """Divergence is detected after every epoch and raises ValueError (L:447-464, L:664)."""
     rng = np.random.RandomState(0)
     train = sp.coo_matrix((rng.rand(40, 30) > 0.5).astype(np.float32) * 1e9)
     feats = sp.csr_matrix(rng.rand(30, 10).astype(np.float32) * 1e9)
+    # replay mode is deterministic: this configuration overflows within five epochs
+    with pytest.raises(ValueError):
+        LightFM(loss="logistic", learning_rate=1e6, no_components=4, random_state=0).fit(
+            train, item_features=feats, epochs=5, num_threads=1)
+    # both modes: a non-finite parameter is caught by the per-epoch check (on the device in the
+    # resident path) whatever the training dynamics are
+    ident = H.synthetic_interactions(80, 60, 1500, 2)
     for nt in (1, 4):
-        with pytest.raises(ValueError):
-            LightFM(loss="logistic", learning_rate=1e6, no_components=4).fit(
-                train, item_features=feats, epochs=5, num_threads=nt)
+        for loss in ("warp", "logistic"):
+            model = LightFM(loss=loss, no_components=16, random_state=0).fit(ident, epochs=1, num_threads=nt)
+            model.item_embeddings[3, 2] = np.inf
+            with pytest.raises(ValueError):
+                model.fit_partial(ident, epochs=2, num_threads=nt)
 
 
 def test_warp_few_items_stays_finite():  # tests/test_api.py:374-382

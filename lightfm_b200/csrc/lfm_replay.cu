@@ -88,9 +88,19 @@ __device__ void gather2(const DevCsr& fa, const float* ea, const float* ba, int 
 }
 
 // T:320-334: strictly left-to-right fp32 sum; every lane computes the same value.
+// The adds form one dependent chain by definition; the loads and products do not, so they are
+// issued eight at a time ahead of the chain (same operations, same order of additions).
 __device__ float score(const float* u, const float* v, int d) {
     float r = u[d] + v[d];
-    for (int i = 0; i < d; i++) r = r + u[i] * v[i];
+    int i = 0;
+    for (; i + 8 <= d; i += 8) {
+        float p[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) p[k] = u[i + k] * v[i + k];
+#pragma unroll
+        for (int k = 0; k < 8; k++) r = r + p[k];
+    }
+    for (; i < d; i++) r = r + u[i] * v[i];
     return r;
 }
 
@@ -174,12 +184,58 @@ __device__ void warp_update(FitArgs& a, double loss, int user, int pos_id, int n
         b1 = bias_steps(a.itf, neg_id, m.item, loss, m, a.item_alpha);
         b2 = bias_steps(a.usf, user, m.user, loss, m, a.user_alpha);
     }
-    for (int i = lane; i < d; i += 32) {
-        float uc = sh.u[i], pc = sh.pos[i], nc = sh.neg[i];
-        sh.lrsum[3 * i + 0] = row_steps(a.itf, pos_id, m.item, i, (-loss) * (double)uc, m, a.item_alpha);
-        sh.lrsum[3 * i + 1] = row_steps(a.itf, neg_id, m.item, i, loss * (double)uc, m, a.item_alpha);
-        sh.lrsum[3 * i + 2] = row_steps(a.usf, user, m.user, i, loss * (double)(float)(nc - pc), m,
-                                        a.user_alpha);
+    if (a.itf.identity && a.usf.identity && pos_id != neg_id && d <= 256) {
+        // Identity features: the nine values a component's three steps touch (w, G, M of the
+        // positive, negative and user rows) are private to this lane and distinct, so they are
+        // fetched up front for all of the lane's components -- one overlapped L2 round trip
+        // instead of a dependent one per step -- then stepped in the reference's order and
+        // stored.  The arithmetic is step()'s, untouched.
+        constexpr int KMAX = 8;
+        float w[KMAX][3], g[KMAX][3], mo[KMAX][3];
+        const size_t op = (size_t)pos_id * d, on = (size_t)neg_id * d, ou = (size_t)user * d;
+#pragma unroll
+        for (int k = 0; k < KMAX; k++) {
+            const int i = lane + 32 * k;
+            if (i < d) {
+                w[k][0] = m.item.w[op + i]; g[k][0] = m.item.g[op + i];
+                w[k][1] = m.item.w[on + i]; g[k][1] = m.item.g[on + i];
+                w[k][2] = m.user.w[ou + i]; g[k][2] = m.user.g[ou + i];
+                if (m.adadelta) {
+                    mo[k][0] = m.item.m[op + i]; mo[k][1] = m.item.m[on + i]; mo[k][2] = m.user.m[ou + i];
+                } else {
+                    mo[k][0] = mo[k][1] = mo[k][2] = 0.0f;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < KMAX; k++) {
+            const int i = lane + 32 * k;
+            if (i < d) {
+                const float uc = sh.u[i], pc = sh.pos[i], nc = sh.neg[i];
+                const double lr = (double)m.lr;
+                sh.lrsum[3 * i + 0] = 0.0 + step(&w[k][0], &g[k][0], &mo[k][0], (double)1.0f, (-loss) * (double)uc,
+                                                 m.adadelta, lr, a.item_alpha, m.rho, m.eps);
+                sh.lrsum[3 * i + 1] = 0.0 + step(&w[k][1], &g[k][1], &mo[k][1], (double)1.0f, loss * (double)uc,
+                                                 m.adadelta, lr, a.item_alpha, m.rho, m.eps);
+                sh.lrsum[3 * i + 2] = 0.0 + step(&w[k][2], &g[k][2], &mo[k][2], (double)1.0f,
+                                                 loss * (double)(float)(nc - pc), m.adadelta, lr, a.user_alpha,
+                                                 m.rho, m.eps);
+                m.item.w[op + i] = w[k][0]; m.item.g[op + i] = g[k][0];
+                m.item.w[on + i] = w[k][1]; m.item.g[on + i] = g[k][1];
+                m.user.w[ou + i] = w[k][2]; m.user.g[ou + i] = g[k][2];
+                if (m.adadelta) {
+                    m.item.m[op + i] = mo[k][0]; m.item.m[on + i] = mo[k][1]; m.user.m[ou + i] = mo[k][2];
+                }
+            }
+        }
+    } else {
+        for (int i = lane; i < d; i += 32) {
+            float uc = sh.u[i], pc = sh.pos[i], nc = sh.neg[i];
+            sh.lrsum[3 * i + 0] = row_steps(a.itf, pos_id, m.item, i, (-loss) * (double)uc, m, a.item_alpha);
+            sh.lrsum[3 * i + 1] = row_steps(a.itf, neg_id, m.item, i, loss * (double)uc, m, a.item_alpha);
+            sh.lrsum[3 * i + 2] = row_steps(a.usf, user, m.user, i, loss * (double)(float)(nc - pc), m,
+                                            a.user_alpha);
+        }
     }
     __syncwarp();
     if (a.item_alpha != 0.0 || a.user_alpha != 0.0) {

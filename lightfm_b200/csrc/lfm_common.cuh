@@ -105,7 +105,6 @@ cudaError_t lfm_launch_check_unit(const float* y, const float* w, int64_t n, int
 cudaError_t lfm_launch_build_bitmap_coo(const int32_t* user_ids, const int32_t* item_ids, int64_t n,
                                         uint32_t* bitmap, int32_t rows, int32_t words_per_row, cudaStream_t st);
 cudaError_t lfm_launch_build_bitmap(const DevCsr& pos, uint32_t* bitmap, int32_t words_per_row, cudaStream_t st);
-size_t lfm_item_repr_scratch_floats(const DevCsr& itf, const DevModel& m);
 
 #ifdef __CUDACC__
 // ---- RNG ---------------------------------------------------------------------

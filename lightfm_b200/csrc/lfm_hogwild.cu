@@ -1,22 +1,20 @@
-// lfm_hogwild.cu -- throughput mode (num_threads > 1): one warp per interaction,
-// lock-free concurrent updates over the whole GPU.
+// lfm_hogwild.cu -- throughput mode (num_threads > 1): lock-free concurrent SGD over the whole GPU.
 //
 // The reference runs the SGD loop under an OpenMP prange with racy, lock-free
-// read-modify-writes on the shared tables (Hogwild; T:825 and SURVEY 0).  Here
-// every warp takes one (user, positive item) tuple:
-//   gather user / item rows (coalesced, L2-coherent ld.global.cg) -> registers
-//   warp-shuffle dot product
-//   Philox4x32 negative draws, WARP rank-sampling loop in registers
-//   Adagrad-scaled deltas scattered with red.global.add (no lost updates)
-// Floating point is fp32 with FMA; results are statistically equivalent to the
-// reference's multi-thread runs, not bit-equal (nor is the reference to itself).
+// read-modify-writes on the shared tables (Hogwild; T:825 and SURVEY 0).  Here the epoch is
+//   1. pack_kernel: tuples[i] = {user, item, weight, y}[order[i]] (order = host shuffle, or a
+//      Feistel bijection of [0, n) generated in registers);
+//   2. one SGD kernel over the tuples: gather user / item rows (L2-coherent ld.global.cg),
+//      dot product by warp shuffles, Philox negative draws, the WARP rank-sampling loop in
+//      registers, Adagrad-scaled deltas scattered with red.global.add (no lost updates).
+// Floating point is fp32 with FMA; results are statistically equivalent to the reference's
+// multi-thread runs, not bit-equal (nor is the reference to itself).
 //
 // Two kernel families:
-//   generic   lanes own components l, l+32, ...; any d <= 256, any feature CSR,
-//             adagrad / adadelta, L2 regularisation.
-//   fast      identity features, adagrad, alpha == 0, d in {16, 32, 64, 128}:
-//             float4 lanes, several rows per load instruction, speculative
-//             negative batches, vector red.global.add.v4.f32 (lfm_hogwild_fast.cuh).
+//   generic (this file)      lanes own components; any d <= 256, any feature CSR, adagrad /
+//                            adadelta, L2 regularisation (log-domain lazy scale).
+//   fast (lfm_hogwild_fast.cuh)  identity features, adagrad, alpha == 0, d in {16,32,64,128}:
+//                            slot-per-interaction kernels with cp.async staging.
 //
 // Reference: fit_logistic T:694-781, fit_warp T:784-912, fit_warp_kos T:915-1071,
 // fit_bpr T:1074-1182, update T:454-534, warp_update T:537-649.

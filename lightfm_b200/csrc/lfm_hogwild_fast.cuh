@@ -3,18 +3,24 @@
 // Eligibility: identity user AND item features, adagrad, item_alpha == user_alpha == 0,
 // no_components d in {16, 32, 64, 128}.  This is BASELINE configs C1, C2, C4, C5.
 //
-// Layout: a row of d floats is read by LPR = d/4 lanes as one float4 each, so a
-// warp covers NS = 32/LPR rows ("slots") per load instruction:
-//     d = 16 -> 8 slots, 32 -> 4, 64 -> 2, 128 -> 1.
-// WARP / k-OS: one warp per interaction.  The user and positive rows are loaded
-// by every slot (same addresses -> one L2 request), then NS negative candidates
-// are scored per round, one per slot, speculatively: the first violating one in
-// draw order wins, exactly as if they had been drawn one at a time (candidates
-// after the winner are discarded and do not count as sampled).
-// Logistic / BPR have no rank-sampling loop: one slot per interaction, NS
-// interactions per warp.
-// Updates: G row is re-read (ld.global.cg.v4), deltas go out as
-// red.global.add.v4.f32 (fire-and-forget vector reductions performed in L2).
+// fast_slot_kernel (WARP / BPR / logistic / k-OS): every interaction owns a SLOT of
+// LPR = d / (4 * VPL) lanes (a lane holds VPL float4 chunks of each row) and NS = 32 / LPR
+// interactions run per warp in lockstep:
+//     d = 64: VPL 2 -> 8 lanes per interaction, 4 interactions per warp (default for WARP)
+//             VPL 1 -> 16 lanes,                2 interactions per warp
+// The user / positive rows and their Adagrad accumulator rows are staged one group ahead with
+// cp.async.cg into double-buffered shared memory; negatives are drawn with Philox4x32-7 and
+// scored one per slot per round; membership in the user's positives is one load from an exact
+// bitmap (resident plans) or an LPR-ary / 4*LPR-ary search of the sorted CSR row; updates are
+// red.global.add.v4.f32 reductions performed in L2 (fire and forget).
+//
+// fast_rank_kernel (first generation; k-OS with n > LPR, and WARP under lfm_set_tuning(0)):
+// one warp per interaction, the user and positive rows loaded by every slot, NS negative
+// candidates scored per round speculatively -- the first violating one in draw order wins,
+// exactly as if they had been drawn one at a time.
+//
+// How the design moved from the second to the first is recorded with the ncu captures in
+// profiles/README.md.
 #pragma once
 
 namespace {

@@ -245,10 +245,6 @@ cudaError_t lfm_launch_predict(const DevCsr& itf, const DevCsr& usf, const DevMo
     return cudaGetLastError();
 }
 
-size_t lfm_item_repr_scratch_floats(const DevCsr& itf, const DevModel& m) {
-    // transposed item table + one score row per resident CTA
-    return (size_t)itf.rows * (m.d + 1);
-}
 
 cudaError_t lfm_launch_predict_ranks(const DevCsr& itf, const DevCsr& usf, const DevCsr& test,
                                      const DevCsr& train, const DevModel& m, float* ranks,

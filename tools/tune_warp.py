@@ -8,7 +8,7 @@ import bench as B  # noqa: E402
 from lightfm_b200 import _lightfm_fast as fast  # noqa: E402
 
 fast.set_mode("hogwild")
-variants = [int(v) for v in (sys.argv[1].split(",") if len(sys.argv) > 1 else "0,1,2,3".split(","))]
+variants = [int(v) for v in (sys.argv[1].split(",") if len(sys.argv) > 1 else "0,4,5,6,7,8".split(","))]
 nnz = int(sys.argv[2]) if len(sys.argv) > 2 else B.NNZ
 prob = B.Problem(B.N_USERS, B.N_ITEMS, nnz, B.D, seed=2, device="cuda")
 itf, usf, pos = fast.CSRMatrix(prob.itf), fast.CSRMatrix(prob.usf), fast.CSRMatrix(prob.pos)

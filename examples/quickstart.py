@@ -3,9 +3,13 @@ doc/quickstart.rst, on synthetic data since there is no network for MovieLens).
 
     python examples/quickstart.py
 """
+import os
+import sys
 import time
 
 import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # run from a checkout
 
 from lightfm_b200 import LightFM
 from lightfm_b200.cross_validation import random_train_test_split

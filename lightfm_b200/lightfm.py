@@ -238,6 +238,14 @@ class LightFM(object):
         interactions = interactions.tocoo()
         if interactions.dtype != CYTHON_DTYPE:
             interactions.data = interactions.data.astype(CYTHON_DTYPE)
+        if interactions.row.dtype != np.int32 or interactions.col.dtype != np.int32:
+            # scipy switches to int64 indices for very large matrices; the native layer is int32
+            # like the reference's (nnz and both dimensions must stay below 2**31)
+            if max(interactions.shape) >= 2 ** 31:
+                raise ValueError("interaction matrices with a dimension >= 2**31 are not supported")
+            interactions = sp.coo_matrix(
+                (interactions.data, (interactions.row.astype(np.int32), interactions.col.astype(np.int32))),
+                shape=interactions.shape)
 
         sample_weight_data = self._process_sample_weight(interactions, sample_weight)
 

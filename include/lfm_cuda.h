@@ -32,9 +32,10 @@
  *        num_threads == 1  -> LFM_MODE_REPLAY : one sequential stream, the
  *                             reference's exact order, rand_r stream and
  *                             per-element arithmetic (bit-reproducible);
- *        num_threads  > 1  -> LFM_MODE_HOGWILD: one warp per interaction,
- *                             lock-free concurrent updates (the reference's
- *                             OpenMP semantics, scaled to the whole GPU).
+ *        num_threads  > 1  -> LFM_MODE_HOGWILD: thousands of interactions in
+ *                             flight over the whole GPU (a slot of 4-32 lanes
+ *                             each), lock-free concurrent updates (the
+ *                             reference's OpenMP semantics, scaled up).
  */
 #ifndef LFM_CUDA_H
 #define LFM_CUDA_H
@@ -124,6 +125,25 @@ int lfm_get_mode(void);
 int lfm_set_bitmap_limit(int64_t bytes);
 /* Free the cached device staging buffers held by the host entry points. */
 int lfm_release_cache(void);
+/* Page-lock / unlock caller-owned host memory in place (cudaHostRegister), for buffers that
+ * outlive one call (the model's state arrays across fit_partial calls).  The caller must
+ * unpin before the memory is freed. */
+int lfm_pin_host(void *ptr, int64_t bytes);
+int lfm_unpin_host(void *ptr);
+
+/* ---- tuning / test knobs (process-wide; each returns the previous value) ------------ */
+/* WARP slot-kernel variant: 0 first-generation warp-per-interaction kernel; 4/5 one float4 per
+ * lane at 3/4 CTAs per SM; 6/7/8 two float4 per lane at 2/3/4 CTAs per SM (default 7). */
+int lfm_set_tuning(int variant);
+/* 0: route fast-path-eligible problems through the generic kernels (tests). */
+int lfm_set_fast_path(int enabled);
+/* Hogwild launches keep at most max(64, n / divisor) interactions in flight (default 128). */
+int lfm_set_inflight_divisor(int divisor);
+/* 0: disable the per-CTA shared-memory aggregation of hot feature rows (feature path; tests / A-B timing). */
+int lfm_set_hot_rows(int enabled);
+/* 1: run the slot kernels as ONE warp with ONE interaction in flight and the reference's rand_r
+ * negatives, so that only their arithmetic differs from the oracle (tests/test_gpu_probe.py). */
+int lfm_set_probe(int enabled);
 
 /* ---- host entry points: the drop-in boundary ------------------------------ */
 
@@ -204,6 +224,9 @@ int lfm_plan_create(lfm_plan **out, int32_t loss, const lfm_csr *item_features,
 int lfm_plan_epoch(lfm_plan *plan, const int32_t *shuffle_indices, uint32_t seed,
                    int32_t num_threads, lfm_counters *counters);
 int lfm_plan_download(lfm_plan *plan, lfm_model *model);
+/* Refresh the resident state arrays and scalar hyper-parameters from `model` (shapes must equal
+ * the plan's); interactions, features and the positives lookup stay as uploaded. */
+int lfm_plan_upload_model(lfm_plan *plan, const lfm_model *model);
 /* Device address and element count of one resident state array (for the caller's own
  * collectives): which = 0..5 item {w,g,m,b,bg,bm}, 6..11 user {w,g,m,b,bg,bm}. */
 int lfm_plan_table(lfm_plan *plan, int32_t which, void **dev_ptr, int64_t *count);

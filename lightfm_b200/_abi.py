@@ -107,6 +107,14 @@ LIB_ONLY = {
                                   C.c_int32, C.c_int32]),
     "lfm_plan_epoch": (C.c_int, [C.c_void_p, c_i32p, C.c_uint32, C.c_int32, CountersP]),
     "lfm_plan_download": (C.c_int, [C.c_void_p, ModelP]),
+    "lfm_plan_upload_model": (C.c_int, [C.c_void_p, ModelP]),
+    "lfm_pin_host": (C.c_int, [C.c_void_p, C.c_int64]),
+    "lfm_unpin_host": (C.c_int, [C.c_void_p]),
+    "lfm_set_tuning": (C.c_int, [C.c_int]),
+    "lfm_set_fast_path": (C.c_int, [C.c_int]),
+    "lfm_set_inflight_divisor": (C.c_int, [C.c_int]),
+    "lfm_set_probe": (C.c_int, [C.c_int]),
+    "lfm_set_hot_rows": (C.c_int, [C.c_int]),
     "lfm_plan_table": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "lfm_plan_check_finite": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "lfm_plan_set_global_items": (C.c_int, [C.c_void_p, C.c_int32]),

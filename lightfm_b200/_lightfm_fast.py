@@ -12,7 +12,8 @@ if no CUDA device is usable every compute call raises ``RuntimeError``.
 
 Execution mode (``num_threads`` has no natural meaning on a GPU):
   ``num_threads == 1``  deterministic replay of the reference's single-thread order
-  ``num_threads  > 1``  hogwild throughput mode (one warp per interaction)
+  ``num_threads  > 1``  hogwild throughput mode (thousands of interactions in flight, a slot of
+                        4-32 lanes each, lock-free updates)
 override with ``LIGHTFM_CUDA_MODE=replay|hogwild|auto`` or :func:`set_mode`.
 """
 import ctypes
@@ -62,6 +63,12 @@ def device_count():
     return _lib.lfm_device_count()
 
 
+def set_device(device):
+    """Select the CUDA device of this process (before the first compute call; one process per
+    GPU).  Raises if the library was already initialised on another device."""
+    _check(_lib.lfm_set_device(int(device)))
+
+
 def resolves_to_hogwild(num_threads):
     """True when a fit call with this num_threads runs the throughput kernels."""
     mode = _lib.lfm_get_mode()
@@ -70,27 +77,29 @@ def resolves_to_hogwild(num_threads):
 
 def set_fast_path(enabled):
     """Testing hook: disable the specialised hogwild kernels (generic ones run instead)."""
-    fn = _lib.lfm_set_fast_path
-    fn.restype = ctypes.c_int
-    fn.argtypes = [ctypes.c_int]
-    return fn(int(bool(enabled)))
+    return _lib.lfm_set_fast_path(int(bool(enabled)))
+
+
+def set_probe(enabled):
+    """Testing hook: run the slot kernels as one warp with one interaction in flight and the
+    reference's rand_r negatives (tests/test_gpu_probe.py: arithmetic-only comparison with the oracle)."""
+    return _lib.lfm_set_probe(int(bool(enabled)))
+
+
+def set_hot_rows(enabled):
+    """Feature path: per-CTA shared-memory aggregation of hot feature rows (default on)."""
+    return _lib.lfm_set_hot_rows(int(bool(enabled)))
 
 
 def set_inflight_divisor(divisor):
     """Hogwild launches keep at most max(64, n / divisor) interactions in flight (default 128)."""
-    fn = _lib.lfm_set_inflight_divisor
-    fn.restype = ctypes.c_int
-    fn.argtypes = [ctypes.c_int]
-    return fn(int(divisor))
+    return _lib.lfm_set_inflight_divisor(int(divisor))
 
 
 def set_tuning(variant):
     """WARP fast-path kernel variant: 0 = warp per interaction (v1); 4/5 = slot per interaction,
     one float4 per lane, 3/4 CTAs per SM; 6/7/8 = two float4 per lane, 2/3/4 CTAs per SM."""
-    fn = _lib.lfm_set_tuning
-    fn.restype = ctypes.c_int
-    fn.argtypes = [ctypes.c_int]
-    return fn(int(variant))
+    return _lib.lfm_set_tuning(int(variant))
 
 
 _TUNING_NAMES = {0: "fast_rank_kernel<WARP,LPR=d/4>", 4: "fast_slot_kernel<WARP,d,1,3>", 5: "fast_slot_kernel<WARP,d,1,4>",
@@ -120,6 +129,34 @@ def set_bitmap_limit(nbytes):
 
 def release_cache():
     _check(_lib.lfm_release_cache())
+
+
+class PinnedArrays(object):
+    """Page-lock a set of long-lived numpy arrays in place (cudaHostRegister) and keep them alive
+    until ``release()``: memory must never be freed while it is registered."""
+
+    def __init__(self, arrays):
+        self.arrays = []
+        for a in arrays:
+            if a is None or a.nbytes == 0:
+                continue
+            if _lib.lfm_pin_host(ctypes.c_void_p(a.ctypes.data), a.nbytes) == 0:
+                self.arrays.append(a)
+
+    def holds(self, arrays):
+        have = {id(a) for a in self.arrays}
+        return all(a is None or a.nbytes == 0 or id(a) in have for a in arrays)
+
+    def release(self):
+        for a in self.arrays:
+            _lib.lfm_unpin_host(ctypes.c_void_p(a.ctypes.data))
+        self.arrays = []
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
 
 
 if os.environ.get("LIGHTFM_CUDA_INFLIGHT_DIVISOR"):
@@ -208,6 +245,12 @@ class ResidentPlan(object):
 
     def download(self):
         _check(_lib.lfm_plan_download(self._handle, self._lightfm.ptr))
+
+    def upload_model(self, lightfm):
+        """Refresh the resident state from the arrays of `lightfm` (same shapes as the plan's);
+        later ``download()`` calls write into these arrays."""
+        _check(_lib.lfm_plan_upload_model(self._handle, lightfm.ptr))
+        self._lightfm = lightfm
 
     def all_finite(self):
         ok = ctypes.c_int32(0)

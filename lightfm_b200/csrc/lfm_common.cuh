@@ -73,6 +73,8 @@ struct FitArgs {
     int32_t k, nkos;               // k-OS parameters
     uint32_t seed;                 // rand_r seed (replay) / philox key (hogwild)
     const double* loss_table;      // [max_sampled + 1] log terms precomputed on the host
+    const float* loss_table_f;     // the same terms rounded to float (hogwild kernels)
+    int64_t t_offset;              // index of this launch's first tuple in the epoch (Philox counter base)
     DevCounters* counters;
     DevScales* scales;
     // Optional exact membership bitmap of the positives CSR: bit (u, i) at
@@ -80,6 +82,13 @@ struct FitArgs {
     // it fits (lfm_launch_build_bitmap); the kernels fall back to the sorted-row search when null.
     const uint32_t* pos_bitmap;
     int32_t bitmap_words;
+    // Hot feature rows (lfm_hogwild.cu, feature path): rows shared by many entities (tags) whose
+    // updates are aggregated per CTA in shared memory before they reach L2.  hot_slot_*[row] is
+    // the row's slot (or -1); hot_rows[slot] = row | (user table ? 1 << 31 : 0).
+    const int32_t* hot_slot_item;
+    const int32_t* hot_slot_user;
+    const int32_t* hot_rows;
+    int32_t n_hot;
     // 1 when every Y and every sample weight equals 1.0f (checked on the device when the inputs
     // are staged): pack_kernel then skips two of its three random reads per interaction.
     int32_t unit_weights;
@@ -101,10 +110,20 @@ cudaError_t lfm_launch_auc(const DevCsr& ranks, const int32_t* num_train_pos, fl
 cudaError_t lfm_launch_in_positives(const DevCsr& mat, int32_t row, int32_t col, int32_t* out,
                                     cudaStream_t st);
 cudaError_t lfm_launch_check_identity(const DevCsr& m, int32_t* flag, cudaStream_t st);
+// Per-feature-row touch counts of one epoch (positives' rows once per interaction, plus
+// `neg_per_item` for every row of every item: uniform negatives), for hot-row selection.
+cudaError_t lfm_launch_feature_counts(const FitArgs& a, int loss, float* cnt_item, float* cnt_user,
+                                      float neg_per_item, cudaStream_t st);
 cudaError_t lfm_launch_check_unit(const float* y, const float* w, int64_t n, int32_t* flag, cudaStream_t st);
 cudaError_t lfm_launch_build_bitmap_coo(const int32_t* user_ids, const int32_t* item_ids, int64_t n,
                                         uint32_t* bitmap, int32_t rows, int32_t words_per_row, cudaStream_t st);
 cudaError_t lfm_launch_build_bitmap(const DevCsr& pos, uint32_t* bitmap, int32_t words_per_row, cudaStream_t st);
+// internal helpers shared between translation units (not part of the C ABI)
+size_t lfm_ranks_scratch_floats(int n_items, int d, int test_rows);
+int lfm_hogwild_supported(int loss, int d, int nkos);
+// 1 when the hogwild launch of (loss, a) would take the slot kernels (identity features, adagrad,
+// no L2, d in {16,32,64,128}); plans without a positives CSR can only run there.
+int lfm_fast_path_eligible(int loss, const FitArgs& a, int64_t count);
 
 #ifdef __CUDACC__
 // ---- RNG ---------------------------------------------------------------------

@@ -18,6 +18,8 @@
 //
 // Reference: fit_logistic T:694-781, fit_warp T:784-912, fit_warp_kos T:915-1071,
 // fit_bpr T:1074-1182, update T:454-534, warp_update T:537-649.
+#include <atomic>
+
 #include "lfm_common.cuh"
 
 namespace {
@@ -228,14 +230,260 @@ __device__ __forceinline__ float scatter(const DevCsr& f, DevTable& t, const Dev
     return lrsum;
 }
 
+
+// ---- feature path: batched row traffic + CTA-level aggregation of hot rows ----------------
+// With shared feature rows (tags) the epoch is bound by L2 serialising same-line reductions:
+// a tag carried by 40% of the items receives ~0.7 row-updates per interaction, i.e. ~10^7
+// reductions per epoch on each of its eight 128 B lines, all processed one after another by one
+// L2 slice (C3: 367 ms per epoch, 0.24 of the HBM roofline).  The HOT variant keeps, per CTA,
+// a shared-memory accumulator (delta of w, delta of G, bias deltas) for the n_hot most-touched
+// feature rows; a warp adds its update under a per-slot spin lock with plain vector
+// loads/stores (shared memory has no vector atomics), and every warp flushes one slot per
+// interaction with a single red.global per chunk, so a hot line sees one reduction per
+// ~K/warps interactions of a CTA instead of one per touch.  A lock that cannot be taken within
+// a few tries falls back to the direct global reduction: never a wait, never a lost update.
+// Forward reads use the global rows (missing at most the deltas pending in shared memory:
+// the same order of staleness as the interactions in flight).
+struct HotSmem {
+    float4* acc;   // [n_hot][2 * d4 + 1]: w-delta chunks, G-delta chunks, {db, dbg, -, -}
+    int* locks;    // [n_hot]
+    int stride;    // float4 per slot = 2 * d4 + 1
+    int d4;        // float4 chunks per row = d / 4
+};
+
+__device__ __forceinline__ bool hot_lock(int* lock, int lane) {
+    int got = 0;
+    if (lane == 0) {
+#pragma unroll 1
+        for (int tries = 0; tries < 16 && !got; tries++) got = atomicCAS(lock, 0, 1) == 0;
+    }
+    got = __shfl_sync(LFM_FULL, got, 0);
+    if (got) __threadfence_block();  // acquire
+    return got != 0;
+}
+__device__ __forceinline__ void hot_unlock(int* lock, int lane) {
+    __threadfence_block();  // release: this warp's stores to the slot before the lock word
+    __syncwarp();
+    if (lane == 0) atomicExch(lock, 0);
+}
+
+// Drain one slot into the global tables (called with the slot locked, or after the final barrier).
+template <int NCH>
+__device__ __forceinline__ void hot_drain(const HotSmem& h, int slot, const FitArgs& a, int lane) {
+    const int32_t tag = __ldg(a.hot_rows + slot);
+    const DevTable& t = (tag < 0) ? a.model.user : a.model.item;
+    const int row = tag & 0x7fffffff;
+    float4* base = h.acc + (size_t)slot * h.stride;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < NCH; j++) {
+        const int c = lane + 32 * j;
+        if (c < h.d4) {
+            const float4 dw = base[c], dg = base[h.d4 + c];
+            if (dg.x != 0.f || dg.y != 0.f || dg.z != 0.f || dg.w != 0.f) {
+                base[c] = z;
+                base[h.d4 + c] = z;
+                red_add_v4(t.w + (size_t)row * a.model.d + c * 4, dw.x, dw.y, dw.z, dw.w);
+                red_add_v4(t.g + (size_t)row * a.model.d + c * 4, dg.x, dg.y, dg.z, dg.w);
+            }
+        }
+    }
+    if (lane == 0) {
+        const float4 db = base[2 * h.d4];
+        if (db.y != 0.f) {
+            base[2 * h.d4] = z;
+            red_add(t.b + row, db.x);
+            red_add(t.bg + row, db.y);
+        }
+    }
+}
+
+// Gather in the float4 layout with the row loads of up to four features in flight at a time
+// (the generic gather walks the features one dependent round trip after the other).
+template <int KPL>
+__device__ __forceinline__ void gather_b(const DevCsr& f, const DevTable& t, int d, int row,
+                                         Repr<KPL>& r, int lane) {
+    constexpr int NCH = KPL / 4;
+#pragma unroll
+    for (int k = 0; k < KPL; k++) r.v[k] = 0.0f;
+    r.b = 0.0f;
+    const int d4 = d >> 2;
+    if (f.identity) {
+#pragma unroll
+        for (int j = 0; j < NCH; j++) {
+            const int c = lane + 32 * j;
+            if (c < d4) {
+                const float4 x = ldcg4(t.w + (size_t)row * d + c * 4);
+                r.v[4 * j] = x.x; r.v[4 * j + 1] = x.y; r.v[4 * j + 2] = x.z; r.v[4 * j + 3] = x.w;
+            }
+        }
+        r.b = __ldcg(t.b + row);
+        return;
+    }
+    const int start = __ldg(f.indptr + row), stop = __ldg(f.indptr + row + 1);
+    float bsum = 0.0f;
+    for (int base = start; base < stop; base += 32) {
+        const int cnt = min(32, stop - base);
+        const int my_ft = lane < cnt ? __ldg(f.indices + base + lane) : 0;
+        const float my_fw = lane < cnt ? __ldg(f.data + base + lane) : 0.0f;
+        if (lane < cnt) bsum = fmaf(my_fw, __ldcg(t.b + my_ft), bsum);
+        for (int i0 = 0; i0 < cnt; i0 += 4) {
+            float4 x[4][NCH];
+            float w[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int i = i0 + k;
+                const int ft = __shfl_sync(LFM_FULL, my_ft, i & 31);
+                w[k] = __shfl_sync(LFM_FULL, my_fw, i & 31);
+                if (i >= cnt) w[k] = 0.0f;
+#pragma unroll
+                for (int j = 0; j < NCH; j++) {
+                    const int c = lane + 32 * j;
+                    x[k][j] = (i < cnt && c < d4) ? ldcg4(t.w + (size_t)ft * d + c * 4)
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+#pragma unroll
+                for (int j = 0; j < NCH; j++) {
+                    r.v[4 * j] = fmaf(w[k], x[k][j].x, r.v[4 * j]);
+                    r.v[4 * j + 1] = fmaf(w[k], x[k][j].y, r.v[4 * j + 1]);
+                    r.v[4 * j + 2] = fmaf(w[k], x[k][j].z, r.v[4 * j + 2]);
+                    r.v[4 * j + 3] = fmaf(w[k], x[k][j].w, r.v[4 * j + 3]);
+                }
+            }
+        }
+    }
+    r.b = lfm_warp_sum(bsum);
+}
+
+// Adagrad scatter (alpha == 0) in the float4 layout: accumulator rows of up to four features
+// are fetched together; rows with a hot slot go to the CTA's shared-memory accumulator.
+template <int KPL>
+__device__ __forceinline__ void scatter_b(const DevCsr& f, DevTable& t, const int32_t* __restrict__ hot_slot,
+                                          const HotSmem& h, const DevModel& m, int row,
+                                          const float (&grad)[KPL], float bgrad, int lane) {
+    constexpr int NCH = KPL / 4;
+    const int d = m.d, d4 = d >> 2;
+    const float lr = m.lr;
+    int start, stop;
+    if (f.identity) { start = 0; stop = 1; }
+    else { start = __ldg(f.indptr + row); stop = __ldg(f.indptr + row + 1); }
+    for (int base = start; base < stop; base += 32) {
+        const int cnt = min(32, stop - base);
+        int my_ft = row;
+        float my_fw = 1.0f;
+        if (!f.identity) {
+            my_ft = lane < cnt ? __ldg(f.indices + base + lane) : 0;
+            my_fw = lane < cnt ? __ldg(f.data + base + lane) : 0.0f;
+        }
+        const int my_hs = (hot_slot != nullptr && lane < cnt) ? __ldg(hot_slot + my_ft) : -1;
+        // biases of the rows without a slot: one feature per lane, all in flight together
+        if (lane < cnt && my_hs < 0) {
+            const float g = bgrad * my_fw;
+            const float g0 = __ldcg(t.bg + my_ft);
+            red_add(t.b + my_ft, -lr * rsqrt_ftz(g0) * g);
+            red_add(t.bg + my_ft, g * g);
+        }
+        for (int i0 = 0; i0 < cnt; i0 += 4) {
+            float4 g0[4][NCH];
+            int ft[4], hs[4];
+            float fw[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int i = i0 + k;
+                ft[k] = __shfl_sync(LFM_FULL, my_ft, i & 31);
+                fw[k] = __shfl_sync(LFM_FULL, my_fw, i & 31);
+                hs[k] = __shfl_sync(LFM_FULL, my_hs, i & 31);
+#pragma unroll
+                for (int j = 0; j < NCH; j++) {
+                    const int c = lane + 32 * j;
+                    g0[k][j] = (i < cnt && c < d4) ? ldcg4(t.g + (size_t)ft[k] * d + c * 4)
+                                                   : make_float4(1.f, 1.f, 1.f, 1.f);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (i0 + k >= cnt) break;  // warp-uniform
+                bool in_smem = false;
+                if (hs[k] >= 0) {
+                    int* lock = h.locks + hs[k];
+                    if (hot_lock(lock, lane)) {
+                        float4* sb = h.acc + (size_t)hs[k] * h.stride;
+#pragma unroll
+                        for (int j = 0; j < NCH; j++) {
+                            const int c = lane + 32 * j;
+                            if (c < d4) {
+                                const float gx = grad[4 * j] * fw[k], gy = grad[4 * j + 1] * fw[k],
+                                            gz = grad[4 * j + 2] * fw[k], gw = grad[4 * j + 3] * fw[k];
+                                float4 aw = sb[c], ag = sb[d4 + c];
+                                aw.x -= lr * rsqrt_ftz(g0[k][j].x) * gx; aw.y -= lr * rsqrt_ftz(g0[k][j].y) * gy;
+                                aw.z -= lr * rsqrt_ftz(g0[k][j].z) * gz; aw.w -= lr * rsqrt_ftz(g0[k][j].w) * gw;
+                                ag.x = fmaf(gx, gx, ag.x); ag.y = fmaf(gy, gy, ag.y);
+                                ag.z = fmaf(gz, gz, ag.z); ag.w = fmaf(gw, gw, ag.w);
+                                sb[c] = aw;
+                                sb[d4 + c] = ag;
+                            }
+                        }
+                        if (lane == 0) {
+                            const float g = bgrad * fw[k];
+                            const float bg0 = __ldcg(t.bg + ft[k]);
+                            float4 ab = sb[2 * d4];
+                            ab.x -= lr * rsqrt_ftz(bg0) * g;
+                            ab.y = fmaf(g, g, ab.y);
+                            sb[2 * d4] = ab;
+                        }
+                        hot_unlock(lock, lane);
+                        in_smem = true;
+                    }
+                }
+                if (!in_smem) {
+#pragma unroll
+                    for (int j = 0; j < NCH; j++) {
+                        const int c = lane + 32 * j;
+                        if (c < d4) {
+                            const float gx = grad[4 * j] * fw[k], gy = grad[4 * j + 1] * fw[k],
+                                        gz = grad[4 * j + 2] * fw[k], gw = grad[4 * j + 3] * fw[k];
+                            const size_t o = (size_t)ft[k] * d + c * 4;
+                            red_add_v4(t.w + o, -lr * rsqrt_ftz(g0[k][j].x) * gx, -lr * rsqrt_ftz(g0[k][j].y) * gy,
+                                       -lr * rsqrt_ftz(g0[k][j].z) * gz, -lr * rsqrt_ftz(g0[k][j].w) * gw);
+                            red_add_v4(t.g + o, gx * gx, gy * gy, gz * gz, gw * gw);
+                        }
+                    }
+                    if (hs[k] >= 0 && lane == 0) {  // slot busy: its bias goes the direct way as well
+                        const float g = bgrad * fw[k];
+                        const float bg0 = __ldcg(t.bg + ft[k]);
+                        red_add(t.b + ft[k], -lr * rsqrt_ftz(bg0) * g);
+                        red_add(t.bg + ft[k], g * g);
+                    }
+                }
+            }
+        }
+    }
+}
+
 struct RegState {  // per-warp view of the lazy-regularisation scales (log domain)
     double base_i, base_u;  // last value read from global
     double loc_i, loc_u;    // local contribution not yet flushed
     int pending;
 };
 
-template <int LOSS, int KPL, int VW, bool ADADELTA, bool REG>
-__global__ void __launch_bounds__(256) hogwild_kernel(FitArgs a, const Tuple* __restrict__ tuples) {
+template <int LOSS, int KPL, int VW, bool ADADELTA, bool REG, bool HOT = false>
+__global__ void __launch_bounds__(HOT ? 512 : 256) hogwild_kernel(FitArgs a, const Tuple* __restrict__ tuples) {
+    static_assert(!HOT || (VW == 4 && !ADADELTA && !REG), "the hot-row path is adagrad, alpha == 0, float4 layout");
+    extern __shared__ __align__(16) unsigned char hot_raw[];
+    HotSmem hsm = {nullptr, nullptr, 0, 0};
+    if constexpr (HOT) {
+        hsm.d4 = a.model.d >> 2;
+        hsm.stride = 2 * hsm.d4 + 1;
+        hsm.acc = (float4*)hot_raw;
+        hsm.locks = (int*)(hsm.acc + (size_t)a.n_hot * hsm.stride);
+        const int words = a.n_hot * hsm.stride * 4 + a.n_hot;
+        for (int i = threadIdx.x; i < words; i += blockDim.x) ((int*)hot_raw)[i] = 0;
+        __syncthreads();
+    }
+    int flush_iter = 0;
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -253,31 +501,53 @@ __global__ void __launch_bounds__(256) hogwild_kernel(FitArgs a, const Tuple* __
         rs.base_u = __ldcg(&a.scales->user_scale);
     }
 
-    for (int64_t t = warp; t < a.n; t += nwarps) {
-        Tuple tp = tuples[t];
+#define GATHER(F, T, ROW, SCALE, R)                                          \
+    do {                                                                     \
+        if constexpr (HOT) gather_b<KPL>(F, T, d, ROW, R, lane);             \
+        else gather<KPL, VW>(F, T, d, ROW, SCALE, R, lane);                  \
+    } while (0)
+#define SCATTER(F, T, SLOTS, ROW, GRAD, BGRAD, ALPHA, NNZ)                                        \
+    do {                                                                                          \
+        if constexpr (HOT) { scatter_b<KPL>(F, T, SLOTS, hsm, m, ROW, GRAD, BGRAD, lane); NNZ = 0; } \
+        else lrsum += scatter<KPL, VW, ADADELTA>(F, T, m, ROW, GRAD, BGRAD, ALPHA, lane, NNZ);    \
+    } while (0)
+    for (int64_t tl = warp; tl < a.n; tl += nwarps) {
+        if constexpr (HOT) {
+            // every warp drains one slot per interaction, round robin over the CTA's slots
+            const int wpb = blockDim.x >> 5;
+            const int slot = (int)(((unsigned)flush_iter * (unsigned)wpb + (threadIdx.x >> 5)) % (unsigned)a.n_hot);
+            flush_iter++;
+            if (hot_lock(hsm.locks + slot, lane)) {
+                hot_drain<KPL / 4>(hsm, slot, a, lane);
+                hot_unlock(hsm.locks + slot, lane);
+            }
+        }
+        Tuple tp = tuples[tl];
         if (tp.user < 0) continue;
+        const int64_t t = tl + a.t_offset;  // index in the epoch: segments must not replay one stream
         float item_scale = 1.0f, user_scale = 1.0f;
         if (REG) {
-            item_scale = (float)exp(rs.base_i + rs.loc_i);
-            user_scale = (float)exp(rs.base_u + rs.loc_u);
+            // clamped well above the ln(1e6) rescale trigger and below float overflow (e^88)
+            item_scale = (float)exp(fmin(rs.base_i + rs.loc_i, 60.0));
+            user_scale = (float)exp(fmin(rs.base_u + rs.loc_u, 60.0));
         }
         const int user = tp.user;
         Repr<KPL> u, p, q;
-        gather<KPL, VW>(a.usf, m.user, d, user, user_scale, u, lane);
+        GATHER(a.usf, m.user, user, user_scale, u);
         float lrsum = 0.0f;
         int nnz_total = 0;
         bool updated = false;
 
         if (LOSS == LOSS_LOGISTIC) {
-            gather<KPL, VW>(a.itf, m.item, d, tp.item, item_scale, p, lane);
+            GATHER(a.itf, m.item, tp.item, item_scale, p);
             float pred = 1.0f / (1.0f + __expf(-dot<KPL>(u, p)));
             float loss = tp.weight * (pred - (tp.y > 0 ? 1.0f : 0.0f));
             float gi[KPL], gu[KPL];
 #pragma unroll
             for (int k = 0; k < KPL; k++) { gi[k] = loss * u.v[k]; gu[k] = loss * p.v[k]; }
             int n1, n2;
-            lrsum += scatter<KPL, VW, ADADELTA>(a.itf, m.item, m, tp.item, gi, loss, alpha_i, lane, n1);
-            lrsum += scatter<KPL, VW, ADADELTA>(a.usf, m.user, m, user, gu, loss, alpha_u, lane, n2);
+            SCATTER(a.itf, m.item, a.hot_slot_item, tp.item, gi, loss, alpha_i, n1);
+            SCATTER(a.usf, m.user, a.hot_slot_user, user, gu, loss, alpha_u, n2);
             nnz_total = n1 + n2;
             updated = true;
             c_pos++; c_upd++;
@@ -305,7 +575,7 @@ __global__ void __launch_bounds__(256) hogwild_kernel(FitArgs a, const Tuple* __
                 float my_val = 0.0f;
                 for (int j = 0; j < no_pos; j++) {
                     int sid = __ldg(a.pos.indices + ps + lfm_bounded(next_u32(), (uint32_t)(pe - ps)));
-                    gather<KPL, VW>(a.itf, m.item, d, sid, item_scale, p, lane);
+                    GATHER(a.itf, m.item, sid, item_scale, p);
                     float s = dot<KPL>(u, p);
                     if (lane == j) { my_idx = sid; my_val = s; }
                 }
@@ -321,10 +591,10 @@ __global__ void __launch_bounds__(256) hogwild_kernel(FitArgs a, const Tuple* __
                 if (src < 0) src = 0;  // NaN scores: fall back to the first sample
                 pos_id = __shfl_sync(LFM_FULL, my_idx, src);
                 pp = __shfl_sync(LFM_FULL, my_val, src);
-                gather<KPL, VW>(a.itf, m.item, d, pos_id, item_scale, p, lane);
+                GATHER(a.itf, m.item, pos_id, item_scale, p);
                 c_pos++;
             } else {
-                gather<KPL, VW>(a.itf, m.item, d, pos_id, item_scale, p, lane);
+                GATHER(a.itf, m.item, pos_id, item_scale, p);
                 pp = dot<KPL>(u, p);
                 c_pos++;
             }
@@ -341,7 +611,7 @@ __global__ void __launch_bounds__(256) hogwild_kernel(FitArgs a, const Tuple* __
                     if (!lfm_warp_member(a.pos.indices, ps, pe, neg_id, lane)) break;
                     c_rej++;
                 } while (tries < 256);
-                gather<KPL, VW>(a.itf, m.item, d, neg_id, item_scale, q, lane);
+                GATHER(a.itf, m.item, neg_id, item_scale, q);
                 float np = dot<KPL>(u, q);
                 loss = tp.weight * (1.0f - 1.0f / (1.0f + __expf(-(pp - np))));
                 updated = true;
@@ -350,7 +620,7 @@ __global__ void __launch_bounds__(256) hogwild_kernel(FitArgs a, const Tuple* __
                 while (sampled < m.max_sampled) {
                     sampled++;
                     int cand = lfm_bounded(next_u32(), (uint32_t)n_items);
-                    gather<KPL, VW>(a.itf, m.item, d, cand, item_scale, q, lane);
+                    GATHER(a.itf, m.item, cand, item_scale, q);
                     float np = dot<KPL>(u, q);
                     c_neg++;
                     if (np > pp - 1.0f) {
@@ -373,9 +643,9 @@ __global__ void __launch_bounds__(256) hogwild_kernel(FitArgs a, const Tuple* __
                     gu[k] = loss * (q.v[k] - p.v[k]);
                 }
                 int n1, n2, n3;
-                lrsum += scatter<KPL, VW, ADADELTA>(a.itf, m.item, m, pos_id, gp, -loss, alpha_i, lane, n1);
-                lrsum += scatter<KPL, VW, ADADELTA>(a.itf, m.item, m, neg_id, gn, loss, alpha_i, lane, n2);
-                lrsum += scatter<KPL, VW, ADADELTA>(a.usf, m.user, m, user, gu, loss, alpha_u, lane, n3);
+                SCATTER(a.itf, m.item, a.hot_slot_item, pos_id, gp, -loss, alpha_i, n1);
+                SCATTER(a.itf, m.item, a.hot_slot_item, neg_id, gn, loss, alpha_i, n2);
+                SCATTER(a.usf, m.user, a.hot_slot_user, user, gu, loss, alpha_u, n3);
                 nnz_total = n1 + n2 + n3;
                 c_upd++;
             }
@@ -397,6 +667,13 @@ __global__ void __launch_bounds__(256) hogwild_kernel(FitArgs a, const Tuple* __
                 rs.pending = 0;
             }
         }
+    }
+#undef GATHER
+#undef SCATTER
+    if constexpr (HOT) {  // no more updates after the barrier: drain everything that is still pending
+        __syncthreads();
+        for (int slot = threadIdx.x >> 5; slot < a.n_hot; slot += blockDim.x >> 5)
+            hot_drain<KPL / 4>(hsm, slot, a, lane);
     }
     if (REG && rs.pending && lane == 0) {
         atomicAdd(&a.scales->item_scale, rs.loc_i);
@@ -429,14 +706,16 @@ __global__ void reset_scales_kernel(DevScales* s) { s->item_scale = 0.0; s->user
 // stale (the reference's OpenMP loop has num_threads <= ~100 in flight).  The grid is therefore
 // capped at max(64, n / divisor) concurrent interactions; a full B200 wave (~4.7k warps) is
 // reached from ~600k interactions per launch.
-static int g_inflight_divisor = 128;
+static std::atomic<int> g_inflight_divisor{128};
+static std::atomic<int> g_hot_enabled{1};
+extern "C" int lfm_set_hot_rows(int enabled) { return g_hot_enabled.exchange(enabled ? 1 : 0); }
 extern "C" int lfm_set_inflight_divisor(int divisor) {
-    int old = g_inflight_divisor;
-    if (divisor >= 1) g_inflight_divisor = divisor;
+    int old = g_inflight_divisor.load();
+    if (divisor >= 1) g_inflight_divisor.store(divisor);
     return old;
 }
 static int64_t lfm_inflight_cap(int64_t count) {
-    int64_t cap = count / g_inflight_divisor;
+    int64_t cap = count / g_inflight_divisor.load();
     return cap < 64 ? 64 : cap;
 }
 namespace {
@@ -446,6 +725,7 @@ cudaError_t launch_generic(const FitArgs& a, const Tuple* tuples, int64_t begin,
                            cudaStream_t st) {
     FitArgs b = a;
     b.n = count;
+    b.t_offset = begin;
     const Tuple* tp = tuples + begin;
     bool reg = (a.item_alpha != 0.0 || a.user_alpha != 0.0);
     int block = 256;
@@ -465,6 +745,28 @@ cudaError_t launch_generic(const FitArgs& a, const Tuple* tuples, int64_t begin,
     } else if (reg) {
         hogwild_kernel<LOSS, KPL, 1, false, true><<<(int)blocks, block, 0, st>>>(b, tp);
     } else if (vec) {
+        if constexpr (KPL == 4) {
+            if (a.n_hot > 0 && g_hot_enabled.load()) {
+                // hot-row variant: 512-thread CTAs, one per SM (the accumulators take most of the
+                // shared memory), persistent warps
+                auto kern = hogwild_kernel<LOSS, 4, 4, false, false, true>;
+                const size_t smem = (size_t)a.n_hot * ((2 * (m.d >> 2) + 1) * sizeof(float4) + sizeof(int));
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                int per_sm = 0;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 512, smem);
+                if (per_sm >= 1) {
+                    int dev = 0, sms = 148;
+                    cudaGetDevice(&dev);
+                    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                    int64_t hb = (int64_t)sms * per_sm, need = (count + 15) / 16, capb = (lfm_inflight_cap(count) + 15) / 16;
+                    if (hb > need) hb = need;
+                    if (hb > capb) hb = capb;
+                    if (hb < 1) hb = 1;
+                    kern<<<(int)hb, 512, smem, st>>>(b, tp);
+                    return cudaGetLastError();
+                }
+            }
+        }
         if constexpr (KPL % 4 == 0) hogwild_kernel<LOSS, KPL, 4, false, false><<<(int)blocks, block, 0, st>>>(b, tp);
     } else {
         hogwild_kernel<LOSS, KPL, 1, false, false><<<(int)blocks, block, 0, st>>>(b, tp);
@@ -496,6 +798,41 @@ cudaError_t launch_generic_kpl(const FitArgs& a, const Tuple* tuples, int64_t be
 
 #include "lfm_hogwild_fast.cuh"
 
+namespace {
+__global__ void feature_count_kernel(FitArgs a, int kos, float* cnt_item, float* cnt_user) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; e < a.n; e += stride) {
+        const int user = a.user_ids[e];
+        // k-OS draws its positive from the user's row of the CSR: the same multiset of items
+        const int item = kos ? a.pos.indices[e] : a.item_ids[e];
+        if (cnt_item && !a.itf.identity)
+            for (int i = a.itf.indptr[item]; i < a.itf.indptr[item + 1]; i++) atomicAdd(cnt_item + a.itf.indices[i], 1.0f);
+        if (cnt_user && !a.usf.identity)
+            for (int i = a.usf.indptr[user]; i < a.usf.indptr[user + 1]; i++) atomicAdd(cnt_user + a.usf.indices[i], 1.0f);
+    }
+}
+__global__ void feature_count_items_kernel(DevCsr itf, float per_item, float* cnt_item) {
+    int item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= itf.rows) return;
+    for (int i = itf.indptr[item]; i < itf.indptr[item + 1]; i++) atomicAdd(cnt_item + itf.indices[i], per_item);
+}
+}  // namespace
+
+cudaError_t lfm_launch_feature_counts(const FitArgs& a, int loss, float* cnt_item, float* cnt_user,
+                                      float neg_per_item, cudaStream_t st) {
+    cudaError_t e = cudaSuccess;
+    if (cnt_item) e = cudaMemsetAsync(cnt_item, 0, sizeof(float) * (size_t)a.model.item.n, st);
+    if (e == cudaSuccess && cnt_user) e = cudaMemsetAsync(cnt_user, 0, sizeof(float) * (size_t)a.model.user.n, st);
+    if (e != cudaSuccess || a.n == 0) return e;
+    int64_t blocks = (a.n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    feature_count_kernel<<<(int)blocks, 256, 0, st>>>(a, loss == LOSS_KOS ? 1 : 0, cnt_item, cnt_user);
+    if (cnt_item && !a.itf.identity && loss != LOSS_LOGISTIC && neg_per_item > 0)
+        feature_count_items_kernel<<<(a.itf.rows + 255) / 256, 256, 0, st>>>(a.itf, neg_per_item, cnt_item);
+    return cudaGetLastError();
+}
+
 cudaError_t lfm_launch_check_unit(const float* y, const float* w, int64_t n, int32_t* flag, cudaStream_t st) {
     int64_t blocks = (n + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
@@ -524,7 +861,7 @@ cudaError_t lfm_launch_build_bitmap(const DevCsr& pos, uint32_t* bitmap, int32_t
 }
 
 // Host-visible helper: is (loss, model, features) eligible for the hogwild path at all?
-extern "C" int lfm_hogwild_supported(int loss, int d, int nkos) {
+int lfm_hogwild_supported(int loss, int d, int nkos) {
     if (d < 1 || d > 256) return 0;
     if (loss == LOSS_KOS && nkos > 32) return 0;
     return 1;
@@ -561,13 +898,27 @@ cudaError_t lfm_launch_hogwild(int loss, const FitArgs& a, Tuple* tuples, cudaSt
         if (ev_train_end) cudaEventRecord(ev_train_end, st);
         return cudaSuccess;
     }
-    int64_t seg = reg ? (int64_t)1 << 21 : a.n;
+    // With L2 the lazy scale grows by at most log1p(alpha * llr) per update (llr <= lr under adagrad,
+    // whose accumulators start at 1): keep a segment short enough that the log-scale cannot pass
+    // ln(1e6) before the check between launches (the reference rescales right after the update
+    // that crosses 1e6, T:901-904).
+    int64_t seg = a.n;
+    if (reg) {
+        const double amax = a.item_alpha > a.user_alpha ? a.item_alpha : a.user_alpha;
+        const double step = amax * (a.model.adadelta ? 1.0 : (double)a.model.lr);
+        double lim = step > 0 ? 13.8 / step : 2097152.0;
+        if (lim > 2097152.0) lim = 2097152.0;
+        if (lim < 16384.0) lim = 16384.0;
+        seg = (int64_t)lim;
+    }
     for (int64_t begin = 0; begin < a.n; begin += seg) {
         int64_t count = (a.n - begin < seg) ? (a.n - begin) : seg;
         bool done = false;
         e = lfm_try_launch_fast(loss, a, tuples, begin, count, st, &done);
         if (e != cudaSuccess) return e;
         if (!done) {
+            // bitmap-only plans carry no positives CSR for the generic kernels to search
+            if (loss != LOSS_LOGISTIC && a.pos.indptr == nullptr) return cudaErrorInvalidValue;
             switch (loss) {
                 case LOSS_LOGISTIC: e = launch_generic_kpl<LOSS_LOGISTIC>(a, tuples, begin, count, st); break;
                 case LOSS_WARP: e = launch_generic_kpl<LOSS_WARP>(a, tuples, begin, count, st); break;

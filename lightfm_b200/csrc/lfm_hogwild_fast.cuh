@@ -224,11 +224,13 @@ __device__ __forceinline__ void adagrad_row4_g(float* w, float* G, const float4&
     red_add_v4(G, gx * gx, gy * gy, gz * gz, gw * gw);
 }
 
+template <int KSR>
 struct TupleScalars {
     float ub, pb;    // user / positive-item bias
     int ps, pe;      // bounds of the user's row in the positives CSR
     int probe;       // lane's first-level probe of that row (key independent, see slot_member)
-    int sid;         // k-OS: the positive item this lane sampled from the user's row
+    int sid[KSR];    // k-OS: the positive items this lane sampled from the user's row
+                     // (sample j of the min(n, nnz_u) lives on lane j % LPR, register j / LPR)
 };
 
 // ---- WARP / BPR / logistic: one SLOT per interaction --------------------------------------
@@ -323,11 +325,20 @@ __device__ __forceinline__ int slot_probe_index(int lo, int hi, int sub) {
     return lo + (int)(((unsigned long long)(unsigned)len * (unsigned)sub) >> LOG);
 }
 
-template <int LOSS, int D, int VPL, int MINB, bool BITMAP = false>
+//
+// PROBE (tests only, lfm_set_probe): the same kernel body run as ONE warp with ONE interaction in
+// flight (slot 0; tuple i sits in group i), rows staged at the top of the iteration instead of one
+// group ahead, and negatives drawn from the reference's sequential rand_r stream instead of
+// Philox.  What is left to differ from the oracle is exactly this kernel's arithmetic (fp32
+// temporaries, FMA, lr * rsqrt.approx(G), float log table) -- tests/test_gpu_probe.py states by
+// how much.
+template <int LOSS, int D, int VPL, int MINB, bool BITMAP = false, int KSR = 1, bool PROBE = false>
 __global__ void __launch_bounds__(256, MINB) fast_slot_kernel(FitArgs a, const Tuple* __restrict__ tuples) {
     constexpr bool PAIRWISE = LOSS != LOSS_LOGISTIC;  // has a negative item and a positives CSR
     constexpr bool KOS = LOSS == LOSS_KOS;            // positive item chosen in-kernel (T:975-1011)
-    static_assert(!KOS || VPL == 1, "k-OS keeps its sampled positives one per lane: VPL must be 1");
+    static_assert(!KOS || VPL == 1, "k-OS keeps its sampled positives KSR per lane: VPL must be 1");
+    static_assert(KOS || KSR == 1, "KSR only matters for k-OS");
+    typedef TupleScalars<KSR> Scalars;
     constexpr int LPR = D / (4 * VPL);
     constexpr int NS = 32 / LPR;
     constexpr int BUFF = 4 * D;  // floats per slot per buffer: u, p, Gu, Gp rows
@@ -347,7 +358,7 @@ __global__ void __launch_bounds__(256, MINB) fast_slot_kernel(FitArgs a, const T
 
     // lane's chunk v of a row starts at float offset (sub + LPR*v)*4: consecutive lanes read
     // consecutive 16 B, so every load instruction of a slot is one contiguous LPR*16 B piece
-    auto stage = [&](const Tuple& tp, float* buf, TupleScalars& sc) {
+    auto stage = [&](const Tuple& tp, float* buf, Scalars& sc) {
         if (tp.user < 0) return;
 #pragma unroll
         for (int v = 0; v < VPL; v++) {
@@ -370,36 +381,53 @@ __global__ void __launch_bounds__(256, MINB) fast_slot_kernel(FitArgs a, const T
             }
         }
         if (KOS) {
-            // lane `sub` draws the sub-th of the min(n, nnz_u) positives sampled with replacement
-            // (T:976-980); the draw only needs the row bounds, so it is prefetched as well.
+            // lane `sub` draws samples sub, sub + LPR, ... of the min(n, nnz_u) positives sampled with
+            // replacement (T:976-980); the draws only need the row bounds, so they are prefetched too.
             // tp.item carries the tuple's index in the epoch (pack_kernel), the Philox counter.
             const int len = sc.pe - sc.ps;
-            const Philox4 r4 = philox7((uint32_t)tp.item, 0u, (uint32_t)(sub >> 2), 1u, a.seed, 0x4c464d31u);
-            const uint32_t r = (sub & 3) == 0 ? r4.x : (sub & 3) == 1 ? r4.y : (sub & 3) == 2 ? r4.z : r4.w;
             sc.pb = 0.0f;
-            sc.sid = (len > 0 && sub < min(a.nkos, len)) ? __ldg(a.pos.indices + sc.ps + lfm_bounded(r, (uint32_t)len)) : 0;
+#pragma unroll
+            for (int rr = 0; rr < KSR; rr++) {
+                const int j = rr * LPR + sub;
+                const Philox4 r4 = philox7((uint32_t)tp.item, 0u, (uint32_t)(j >> 2), 1u, a.seed, 0x4c464d31u);
+                const uint32_t r = (j & 3) == 0 ? r4.x : (j & 3) == 1 ? r4.y : (j & 3) == 2 ? r4.z : r4.w;
+                sc.sid[rr] = (len > 0 && j < min(a.nkos, len)) ? __ldg(a.pos.indices + sc.ps + lfm_bounded(r, (uint32_t)len)) : 0;
+            }
         }
     };
+    // PROBE: tuple i is "group" i and only slot 0 carries it
+    const int n_end = PROBE ? n_tuples * NS : n_tuples;
     auto fetch = [&](int base) -> Tuple {
         Tuple tp = {-1, 0, 0.0f, 0.0f};
+        if (PROBE) {
+            if (base >= 0 && base < n_end && slot == 0) tp = tuples[base / NS];
+            return tp;
+        }
         const int t = base + slot;
         if (base >= 0 && t < n_tuples) tp = tuples[t];
         return tp;
     };
+    uint32_t rr_state = a.seed;  // PROBE: the reference's rand_r stream (T:64-81)
 
     int base = warp * NS;  // first tuple of this warp's group; groups are nwarps*NS apart
-    Tuple cur = fetch(base < n_tuples ? base : -1);
-    TupleScalars cs = {0.f, 0.f, 0, 0, -1, 0};
-    stage(cur, sbuf, cs);
-    cp_async_commit();
+    Tuple cur = fetch(base < n_end ? base : -1);
+    Scalars cs = {0.f, 0.f, 0, 0, -1, {0}};
+    if (!PROBE) {
+        stage(cur, sbuf, cs);
+        cp_async_commit();
+    }
     int flip = 0;
 
-    for (; base < n_tuples; base += nwarps * NS, flip ^= 1) {
+    for (; base < n_end; base += nwarps * NS, flip ^= 1) {
         const int nbase = base + nwarps * NS;
-        Tuple nxt = fetch((nbase > 0 && nbase < n_tuples) ? nbase : -1);
-        TupleScalars ns = {0.f, 0.f, 0, 0, -1, 0};
+        Tuple nxt = fetch((nbase > 0 && nbase < n_end) ? nbase : -1);
+        Scalars ns = {0.f, 0.f, 0, 0, -1, {0}};
         float* buf = sbuf + flip * BUFF;
         float* nbuf = sbuf + (flip ^ 1) * BUFF;
+        if (PROBE) {  // stage now: the previous interaction's update is complete and visible
+            stage(cur, buf, cs);
+            cp_async_commit();
+        }
         cp_async_wait_all();
         __syncwarp();
         const bool valid = cur.user >= 0 && (!KOS || cs.pe > cs.ps);  // k-OS skips empty rows (T:972-973)
@@ -421,33 +449,59 @@ __global__ void __launch_bounds__(256, MINB) fast_slot_kernel(FitArgs a, const T
             //      score of sample j on lane j, take the k-th best in stable descending order ----
             const int no_pos = valid ? min(a.nkos, cs.pe - cs.ps) : 0;
             const int slot0 = slot * LPR;
-            float my_val = 0.0f;
+            float my_val[KSR];
+#pragma unroll
+            for (int rr = 0; rr < KSR; rr++) my_val[rr] = 0.0f;
             int maxn = no_pos;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) maxn = max(maxn, __shfl_xor_sync(LFM_FULL, maxn, o));
-            for (int j = 0; j < maxn; j += 2) {
-                const int sa = __shfl_sync(LFM_FULL, cs.sid, slot0 + min(j, LPR - 1));
-                const int sb = __shfl_sync(LFM_FULL, cs.sid, slot0 + min(j + 1, LPR - 1));
-                const bool aa = j < no_pos, ab = j + 1 < no_pos;
-                float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
-                float ba = 0.0f, bb = 0.0f;
-                if (aa) { ra = ldcg4(m.item.w + (size_t)sa * D + sub * 4); ba = __ldcg(m.item.b + sa); }
-                if (ab) { rb = ldcg4(m.item.w + (size_t)sb * D + sub * 4); bb = __ldcg(m.item.b + sb); }
-                const float va = slot_sum<LPR>(dot4(u[0], ra)) + cs.ub + ba;
-                const float vb = slot_sum<LPR>(dot4(u[0], rb)) + cs.ub + bb;
-                if (sub == j) my_val = va;
-                if (sub == j + 1) my_val = vb;
+#pragma unroll
+            for (int rr = 0; rr < KSR; rr++) {
+                for (int l = 0; l < LPR && rr * LPR + l < maxn; l += 2) {
+                    const int j = rr * LPR + l;
+                    const int sa = __shfl_sync(LFM_FULL, cs.sid[rr], slot0 + l);
+                    const int sb = __shfl_sync(LFM_FULL, cs.sid[rr], slot0 + min(l + 1, LPR - 1));
+                    const bool aa = j < no_pos, ab = l + 1 < LPR && j + 1 < no_pos;
+                    float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
+                    float ba = 0.0f, bb = 0.0f;
+                    if (aa) { ra = ldcg4(m.item.w + (size_t)sa * D + sub * 4); ba = __ldcg(m.item.b + sa); }
+                    if (ab) { rb = ldcg4(m.item.w + (size_t)sb * D + sub * 4); bb = __ldcg(m.item.b + sb); }
+                    const float va = slot_sum<LPR>(dot4(u[0], ra)) + cs.ub + ba;
+                    const float vb = slot_sum<LPR>(dot4(u[0], rb)) + cs.ub + bb;
+                    if (sub == l) my_val[rr] = va;
+                    if (sub == l + 1) my_val[rr] = vb;
+                }
             }
-            int rank = 0;
-            for (int j = 0; j < maxn; j++) {
-                const float vj = __shfl_sync(LFM_FULL, my_val, slot0 + min(j, LPR - 1));
-                rank += (j < no_pos && (vj > my_val || (vj == my_val && j < sub))) ? 1 : 0;
+            // position of every sample in the stable descending order == qsort(reverse_pair_compare)
+            int rank[KSR];
+#pragma unroll
+            for (int rr = 0; rr < KSR; rr++) rank[rr] = 0;
+#pragma unroll
+            for (int r2 = 0; r2 < KSR; r2++) {
+                for (int l = 0; l < LPR && r2 * LPR + l < maxn; l++) {
+                    const int j2 = r2 * LPR + l;
+                    const float vj = __shfl_sync(LFM_FULL, my_val[r2], slot0 + l);
+#pragma unroll
+                    for (int rr = 0; rr < KSR; rr++) {
+                        const int j = rr * LPR + sub;
+                        rank[rr] += (j2 < no_pos && (vj > my_val[rr] || (vj == my_val[rr] && j2 < j))) ? 1 : 0;
+                    }
+                }
             }
             const int sel = min(a.k, no_pos) - 1;
-            const unsigned hit = __ballot_sync(LFM_FULL, valid && sub < no_pos && rank == sel) & slotmask;
+            int hit_sid = cs.sid[0];
+            float hit_val = my_val[0];
+            bool has = false;
+#pragma unroll
+            for (int rr = 0; rr < KSR; rr++) {
+                if (!has && valid && rr * LPR + sub < no_pos && rank[rr] == sel) {
+                    has = true; hit_sid = cs.sid[rr]; hit_val = my_val[rr];
+                }
+            }
+            const unsigned hit = __ballot_sync(LFM_FULL, has) & slotmask;
             const int src = hit ? __ffs(hit) - 1 : slot0;  // NaN scores: fall back to the first sample
-            pos_id = __shfl_sync(LFM_FULL, cs.sid, src);
-            pp = __shfl_sync(LFM_FULL, my_val, src);
+            pos_id = __shfl_sync(LFM_FULL, hit_sid, src);
+            pp = __shfl_sync(LFM_FULL, hit_val, src);
             if (valid) pk = ldcg4(m.item.w + (size_t)pos_id * D + sub * 4);  // T:1005-1011
         } else {
             pp = slot_sum<LPR>(pp) + cs.ub + cs.pb;
@@ -468,7 +522,7 @@ __global__ void __launch_bounds__(256, MINB) fast_slot_kernel(FitArgs a, const T
                     r4 = philox7((uint32_t)t, 0u, (uint32_t)(round >> 2), 0u, a.seed, 0x4c464d31u);
                 const int w = round & 3;
                 const uint32_t r = w == 0 ? r4.x : w == 1 ? r4.y : w == 2 ? r4.z : r4.w;
-                const int cand = lfm_bounded(r, (uint32_t)n_items);
+                const int cand = PROBE ? lfm_rand_r(rr_state) % n_items : lfm_bounded(r, (uint32_t)n_items);
                 float qb = 0.0f;
                 if (active) {
 #pragma unroll
@@ -494,7 +548,7 @@ __global__ void __launch_bounds__(256, MINB) fast_slot_kernel(FitArgs a, const T
                         } else {
                             neg_id = cand;
                             // T:881 (weight * log term) / T:1039 (k-OS: no weight)
-                            loss = fminf((KOS ? 1.0f : cur.weight) * (float)a.loss_table[sampled], (float)LFM_MAX_LOSS);
+                            loss = fminf((KOS ? 1.0f : cur.weight) * __ldg(a.loss_table_f + sampled), (float)LFM_MAX_LOSS);
                         }
                     }
                     active = neg_id < 0 && sampled < max_sampled;
@@ -510,7 +564,8 @@ __global__ void __launch_bounds__(256, MINB) fast_slot_kernel(FitArgs a, const T
                     r4 = philox7((uint32_t)t, 0u, (uint32_t)(round >> 2), 2u, a.seed, 0x4c464d31u);
                 const int w = round & 3;
                 const uint32_t r = w == 0 ? r4.x : w == 1 ? r4.y : w == 2 ? r4.z : r4.w;
-                const int64_t j = (int64_t)(((unsigned long long)r * (unsigned long long)a.n_all) >> 32);
+                const int64_t j = PROBE ? (int64_t)(lfm_rand_r(rr_state) % (int)a.n_all)
+                                        : (int64_t)(((unsigned long long)r * (unsigned long long)a.n_all) >> 32);
                 const int cand = active ? __ldg(a.item_ids + j) : 0;
                 bool member;
                 if (BITMAP) {
@@ -543,8 +598,10 @@ __global__ void __launch_bounds__(256, MINB) fast_slot_kernel(FitArgs a, const T
         if (valid && sub == 0) { c_pos++; c_neg += sampled; }
 
         // ---- prefetch the next group while this one updates ----
-        stage(nxt, nbuf, ns);
-        cp_async_commit();
+        if (!PROBE) {
+            stage(nxt, nbuf, ns);
+            cp_async_commit();
+        }
 
         // ---- update (T:454-534 / T:537-649): rows + biases of a slot, one instruction stream ----
         const bool upd = (LOSS == LOSS_WARP || KOS) ? neg_id >= 0 : valid;
@@ -607,6 +664,10 @@ __global__ void __launch_bounds__(256, MINB) fast_slot_kernel(FitArgs a, const T
         }
         cur = nxt;
         cs = ns;
+        if (PROBE) {  // make this interaction's reductions visible to every lane's next loads
+            __threadfence();
+            __syncwarp();
+        }
     }
     cp_async_wait_all();
 #pragma unroll
@@ -645,13 +706,13 @@ FastGrid fast_grid(K kernel, int64_t warps_wanted, int64_t warps_cap) {
     return g;
 }
 
-template <int LOSS, int D, int VPL, int MINB, bool BITMAP>
+template <int LOSS, int D, int VPL, int MINB, bool BITMAP, int KSR = 1>
 cudaError_t launch_slot_impl(const FitArgs& b, const Tuple* tp, int64_t count, cudaStream_t st) {
     constexpr int LPR = D / (4 * VPL);
     constexpr int NS = 32 / LPR;
     constexpr int BT = 256, WPB = BT / 32;  // threads / warps per block
     const size_t smem = (size_t)WPB * NS * 2 * 4 * D * sizeof(float);
-    auto kern = fast_slot_kernel<LOSS, D, VPL, MINB, BITMAP>;
+    auto kern = fast_slot_kernel<LOSS, D, VPL, MINB, BITMAP, KSR>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BT, smem);
@@ -669,12 +730,24 @@ cudaError_t launch_slot_impl(const FitArgs& b, const Tuple* tp, int64_t count, c
     return cudaGetLastError();
 }
 
-template <int LOSS, int D, int VPL, int MINB>
+template <int LOSS, int D, int VPL, int MINB, int KSR = 1>
 cudaError_t launch_slot(const FitArgs& b, const Tuple* tp, int64_t count, cudaStream_t st) {
     if constexpr (LOSS != LOSS_LOGISTIC) {
-        if (b.pos_bitmap) return launch_slot_impl<LOSS, D, VPL, MINB, true>(b, tp, count, st);
+        if (b.pos_bitmap) return launch_slot_impl<LOSS, D, VPL, MINB, true, KSR>(b, tp, count, st);
     }
-    return launch_slot_impl<LOSS, D, VPL, MINB, false>(b, tp, count, st);
+    return launch_slot_impl<LOSS, D, VPL, MINB, false, KSR>(b, tp, count, st);
+}
+
+// Test hook (lfm_set_probe): one warp, one interaction in flight, rand_r negatives.
+static std::atomic<int> g_probe{0};
+template <int LOSS, int D, int VPL, int MINB>
+cudaError_t launch_probe(const FitArgs& b, const Tuple* tp, cudaStream_t st) {
+    constexpr int NS = 32 / (D / (4 * VPL));
+    const size_t smem = (size_t)NS * 2 * 4 * D * sizeof(float);
+    auto kern = fast_slot_kernel<LOSS, D, VPL, MINB, false, 1, true>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<1, 32, smem, st>>>(b, tp);
+    return cudaGetLastError();
 }
 
 // Kernel variant (lfm_set_tuning), measured on C2 in profiles/README.md:
@@ -685,7 +758,7 @@ cudaError_t launch_slot(const FitArgs& b, const Tuple* tp, int64_t count, cudaSt
 // Also tried and dropped (within +-1.5 % of variant 7 once the bitmap was in): 128-thread blocks
 // at 6-8 CTAs per SM (up to 28 warps / SM), and L2 evict-first cache hints on the tuple stream
 // and the CSR probes.
-static int g_tuning = 7;
+static std::atomic<int> g_tuning{7};
 
 template <int LOSS, int LPR>
 cudaError_t launch_fast(const FitArgs& a, const Tuple* tuples, int64_t begin, int64_t count,
@@ -694,9 +767,20 @@ cudaError_t launch_fast(const FitArgs& a, const Tuple* tuples, int64_t begin, in
     b.n = count;
     const Tuple* tp = tuples + begin;
     constexpr int DD = 4 * LPR;
+    if (g_probe.load()) {  // the templates the probe instantiates are the ones the benches time
+        if (b.pos.indptr == nullptr && LOSS != LOSS_LOGISTIC) return cudaErrorInvalidValue;
+        if constexpr (LOSS == LOSS_WARP && DD == 64) return launch_probe<LOSS, 64, 2, 3>(b, tp, st);
+        if constexpr (LOSS == LOSS_BPR && DD == 64) return launch_probe<LOSS, 64, 1, 4>(b, tp, st);
+        if constexpr (LOSS == LOSS_LOGISTIC && DD == 32) return launch_probe<LOSS, 32, 1, 4>(b, tp, st);
+        return cudaErrorInvalidValue;
+    }
     if constexpr (LOSS == LOSS_KOS) {
-        // slot kernel keeps the n sampled positives one per lane of a slot: needs n <= LPR
+        // slot kernel keeps the n sampled positives KSR per lane of a slot: needs n <= KSR * LPR
+        // (KSR = 3 is instantiated for d = 16 / 32, where the class default n = 10 exceeds LPR)
         if (g_tuning != 0 && a.nkos <= LPR) return launch_slot<LOSS, DD, 1, 4>(b, tp, count, st);
+        if constexpr (LPR <= 8) {
+            if (g_tuning != 0 && a.nkos <= 3 * LPR) return launch_slot<LOSS, DD, 1, 4, 3>(b, tp, count, st);
+        }
         FastGrid g = fast_grid(fast_rank_kernel<LOSS, LPR>, count, lfm_inflight_cap(count));
         fast_rank_kernel<LOSS, LPR><<<g.blocks, g.threads, 0, st>>>(b, tp);
         return cudaGetLastError();
@@ -741,32 +825,38 @@ cudaError_t launch_fast_d(const FitArgs& a, const Tuple* tuples, int64_t begin, 
 }  // namespace
 
 extern "C" int lfm_set_tuning(int variant) {
-    int old = g_tuning;
-    if (variant == 0 || (variant >= 4 && variant <= 8)) g_tuning = variant;
+    int old = g_tuning.load();
+    if (variant == 0 || (variant >= 4 && variant <= 8)) g_tuning.store(variant);
     return old;
 }
 
+extern "C" int lfm_set_probe(int enabled) { return g_probe.exchange(enabled ? 1 : 0); }
+
 // Set by lfm_set_fast_path (tests use it to exercise the generic kernels on fast-eligible inputs).
-static int g_fast_enabled = 1;
+static std::atomic<int> g_fast_enabled{1};
 extern "C" int lfm_set_fast_path(int enabled) {
-    int old = g_fast_enabled;
-    g_fast_enabled = enabled ? 1 : 0;
-    return old;
+    return g_fast_enabled.exchange(enabled ? 1 : 0);
+}
+
+int lfm_fast_path_eligible(int loss, const FitArgs& a, int64_t count) {
+    const DevModel& m = a.model;
+    if (!a.itf.identity || !a.usf.identity) return 0;
+    if (m.adadelta || a.item_alpha != 0.0 || a.user_alpha != 0.0) return 0;
+    if (loss == LOSS_KOS && a.nkos > 32) return 0;
+    if (count > 0x7ff00000LL) return 0;  // the fast kernels index tuples with int32
+    if (m.d != 16 && m.d != 32 && m.d != 64 && m.d != 128) return 0;
+    // float4 path needs 16-byte aligned rows
+    if ((((uintptr_t)m.item.w | (uintptr_t)m.item.g | (uintptr_t)m.user.w | (uintptr_t)m.user.g) & 15) != 0)
+        return 0;
+    return 1;
 }
 
 static cudaError_t lfm_try_launch_fast(int loss, const FitArgs& a, const Tuple* tuples,
                                        int64_t begin, int64_t count, cudaStream_t st, bool* done) {
     *done = false;
-    const DevModel& m = a.model;
     const bool csr_free = loss != LOSS_LOGISTIC && a.pos.indptr == nullptr;  // bitmap-only plan
-    if (!g_fast_enabled && !csr_free) return cudaSuccess;
-    if (!a.itf.identity || !a.usf.identity) return cudaSuccess;
-    if (m.adadelta || a.item_alpha != 0.0 || a.user_alpha != 0.0) return cudaSuccess;
-    if (loss == LOSS_KOS && a.nkos > 32) return cudaSuccess;
-    if (count > 0x7ff00000LL) return cudaSuccess;  // the fast kernels index tuples with int32
-    // float4 path needs 16-byte aligned rows
-    if ((((uintptr_t)m.item.w | (uintptr_t)m.item.g | (uintptr_t)m.user.w | (uintptr_t)m.user.g) & 15) != 0)
-        return cudaSuccess;
+    if (!g_fast_enabled.load() && !csr_free) return cudaSuccess;
+    if (!lfm_fast_path_eligible(loss, a, count)) return cudaSuccess;
     switch (loss) {
         case LOSS_LOGISTIC: return launch_fast_d<LOSS_LOGISTIC>(a, tuples, begin, count, st, done);
         case LOSS_WARP: return launch_fast_d<LOSS_WARP>(a, tuples, begin, count, st, done);

@@ -9,6 +9,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -16,14 +18,11 @@
 
 #include "lfm_common.cuh"
 
-extern "C" size_t lfm_ranks_scratch_floats(int n_items, int d, int test_rows);
-extern "C" int lfm_hogwild_supported(int loss, int d, int nkos);
-
 namespace {
 
 thread_local char g_err[512] = "";
-int g_mode = LFM_MODE_AUTO;
-int64_t g_bitmap_limit_bytes = (int64_t)1 << 30;  // resident plans: membership bitmap if <= 1 GiB
+std::atomic<int> g_mode{LFM_MODE_AUTO};
+std::atomic<int64_t> g_bitmap_limit_bytes{(int64_t)1 << 30};  // resident plans: membership bitmap if <= 1 GiB
 int g_device = 0;
 std::mutex g_mu;  // the staging arena is process-global; host entry points serialise on it
 
@@ -276,7 +275,69 @@ struct Staged {
     int loss = 0;
     Xfer x;
     std::vector<double> table;
+    std::vector<float> table_f;
 };
+
+// Hot feature rows (lfm_hogwild.cu): with shared feature rows (tags) the rows touched by a large
+// share of the interactions get a slot in the kernels' per-CTA shared-memory accumulators.
+// Touch counts come from one pass over the interactions on the device; the selection (at most
+// LFM_MAX_HOT rows touched by >= 1/512 of the interactions, most-touched first) is host work on
+// n_features floats.
+#define LFM_MAX_HOT 160
+int select_hot_rows(int loss, FitArgs& a) {
+    a.hot_slot_item = a.hot_slot_user = a.hot_rows = nullptr;
+    a.n_hot = 0;
+    const DevModel& m = a.model;
+    if ((a.itf.identity && a.usf.identity) || m.adadelta || a.item_alpha != 0.0 || a.user_alpha != 0.0 ||
+        m.d % 4 != 0 || m.d > 128 || a.n < 4096)
+        return LFM_OK;
+    if (loss == LOSS_KOS && !a.pos.indices) return LFM_OK;
+    const size_t ni = (size_t)m.item.n, nu = (size_t)m.user.n;
+    void *ci = nullptr, *cu = nullptr;
+    int rc = arena_get("hot.cnt_item", sizeof(float) * ni, &ci);
+    if (rc != LFM_OK) return rc;
+    rc = arena_get("hot.cnt_user", sizeof(float) * nu, &cu);
+    if (rc != LFM_OK) return rc;
+    const float per_item = a.itf.rows > 0 ? 3.0f * (float)a.n / (float)a.itf.rows : 0.0f;  // ~3 negatives scored per positive
+    CU(lfm_launch_feature_counts(a, loss, a.itf.identity ? nullptr : (float*)ci, a.usf.identity ? nullptr : (float*)cu,
+                                 per_item, g_stream));
+    std::vector<float> hi(a.itf.identity ? 0 : ni), hu(a.usf.identity ? 0 : nu);
+    if (!hi.empty()) CU(cudaMemcpyAsync(hi.data(), ci, sizeof(float) * ni, cudaMemcpyDeviceToHost, g_stream));
+    if (!hu.empty()) CU(cudaMemcpyAsync(hu.data(), cu, sizeof(float) * nu, cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    const float threshold = (float)a.n / 512.0f;
+    std::vector<std::pair<float, int32_t>> cand;  // (count, row | user bit)
+    for (size_t r = 0; r < hi.size(); r++) if (hi[r] >= threshold) cand.push_back({hi[r], (int32_t)r});
+    for (size_t r = 0; r < hu.size(); r++) if (hu[r] >= threshold) cand.push_back({hu[r], (int32_t)(r | 0x80000000u)});
+    if (cand.empty()) return LFM_OK;
+    // shared memory per slot: 2 rows + one float4 of bias deltas + the lock word; keep ~200 KB
+    const size_t per_slot = (size_t)(2 * (m.d / 4) + 1) * 16 + 4;
+    size_t max_slots = (200 * 1024) / per_slot;
+    if (max_slots > LFM_MAX_HOT) max_slots = LFM_MAX_HOT;
+    std::sort(cand.begin(), cand.end(), [](const std::pair<float, int32_t>& x, const std::pair<float, int32_t>& y) {
+        return x.first > y.first || (x.first == y.first && x.second < y.second); });
+    if (cand.size() > max_slots) cand.resize(max_slots);
+    std::vector<int32_t> slot_i(ni, -1), slot_u(nu, -1), rows(cand.size());
+    for (size_t s = 0; s < cand.size(); s++) {
+        rows[s] = cand[s].second;
+        if (cand[s].second < 0) slot_u[(size_t)(cand[s].second & 0x7fffffff)] = (int32_t)s;
+        else slot_i[(size_t)cand[s].second] = (int32_t)s;
+    }
+    Xfer x;
+    int32_t *d_si = nullptr, *d_su = nullptr, *d_rows = nullptr;
+    rc = upload("hot.slot_item", slot_i.data(), ni, &d_si, x);
+    if (rc != LFM_OK) return rc;
+    rc = upload("hot.slot_user", slot_u.data(), nu, &d_su, x);
+    if (rc != LFM_OK) return rc;
+    rc = upload("hot.rows", rows.data(), rows.size(), &d_rows, x);
+    if (rc != LFM_OK) return rc;
+    CU(cudaStreamSynchronize(g_stream));  // the host vectors die with this frame
+    a.hot_slot_item = d_si;
+    a.hot_slot_user = d_su;
+    a.hot_rows = d_rows;
+    a.n_hot = (int32_t)rows.size();
+    return LFM_OK;
+}
 
 // Validate + upload everything one epoch needs.  `with_shuffle`: stage the host shuffle too.
 int stage_fit(int loss, const FitInputs& in, bool with_shuffle, Staged* out) {
@@ -366,6 +427,14 @@ int stage_fit(int loss, const FitInputs& in, bool with_shuffle, Staged* out) {
     rc = upload("fit.loss_table", out->table.data(), out->table.size(), &d_table, x);
     if (rc != LFM_OK) return rc;
     a.loss_table = d_table;
+    out->table_f.assign(out->table.begin(), out->table.end());
+    float* d_table_f = nullptr;
+    rc = upload("fit.loss_table_f", out->table_f.data(), out->table_f.size(), &d_table_f, x);
+    if (rc != LFM_OK) return rc;
+    a.loss_table_f = d_table_f;
+
+    rc = select_hot_rows(loss, a);
+    if (rc != LFM_OK) return rc;
 
     void* p = nullptr;
     rc = arena_get("fit.counters", sizeof(DevCounters), &p);
@@ -763,7 +832,10 @@ extern "C" int lfm_plan_create(lfm_plan** out, int32_t loss, const lfm_csr* item
         // exact membership bitmap of the positives (users x items bits) when it is small enough:
         // replaces the sorted-row search (several L2 sectors per violating negative) by one load
         const DevCsr& pos = p->st.a.pos;
-        const int64_t words = ((int64_t)pos.cols + 31) / 32;
+        // negatives are drawn from [0, item_features.rows), which may exceed interactions.shape[1]
+        // (lightfm.py:314-363 only requires >=): size the rows for the larger, extra columns stay 0
+        const int64_t n_cols = pos.cols > p->st.a.itf.rows ? pos.cols : p->st.a.itf.rows;
+        const int64_t words = (n_cols + 31) / 32;
         const int64_t bytes = words * 4 * (int64_t)pos.rows;
         if (pos.rows > 0 && words > 0 && bytes <= g_bitmap_limit_bytes) {
             void* bm = nullptr;
@@ -804,6 +876,10 @@ extern "C" int lfm_plan_epoch(lfm_plan* p, const int32_t* shuffle_indices, uint3
     struct Restore { ~Restore() { g_cur = &g_arena; } } restore;
     Staged& st = p->st;
     const int mode = resolve_mode(num_threads, p->loss, st.a.model.d, p->nkos);
+    if (p->loss != LOSS_LOGISTIC && st.a.pos.indptr == nullptr &&
+        (mode != LFM_MODE_HOGWILD || !lfm_fast_path_eligible(p->loss, st.a, st.a.n)))
+        return fail(LFM_ERR_STATE, "this plan has no positives CSR (bitmap only): it can only run the "
+                                   "hogwild slot kernels, not replay mode or the generic kernels");
     Xfer x;
     CU(cudaEventRecord(g_ev[0], g_stream));
     if (shuffle_indices) {
@@ -829,6 +905,47 @@ extern "C" int lfm_plan_epoch(lfm_plan* p, const int32_t* shuffle_indices, uint3
     cudaEventElapsedTime(&ms_k, g_ev[1], g_ev[2]);
     cudaEventElapsedTime(&ms_d2h, g_ev[2], g_ev[3]);
     fill_counters(counters, hc, x, launches, mode, ms_h2d, ms_k, ms_d2h);
+    return LFM_OK;
+}
+
+// Refresh the resident model state (and the scalar hyper-parameters) from the caller's arrays;
+// the interactions, feature matrices and positives lookup stay as uploaded.
+extern "C" int lfm_plan_upload_model(lfm_plan* p, const lfm_model* model) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (!p || !model) return fail(LFM_ERR_ARG, "null plan / model");
+    const DevModel& dm = p->st.a.model;
+    if (model->no_components != dm.d || model->n_item_features != dm.item.n ||
+        model->n_user_features != dm.user.n || (model->adadelta != 0) != (dm.adadelta != 0) ||
+        model->max_sampled != dm.max_sampled)
+        return fail(LFM_ERR_ARG, "model shape does not match the plan");
+    g_cur = &p->arena;
+    struct Restore { ~Restore() { g_cur = &g_arena; } } restore;
+    Xfer x;
+    DevModel fresh;
+    int rc = upload_model(model, true, &fresh, x);
+    if (rc != LFM_OK) return rc;
+    p->st.a.model = fresh;
+    CU(cudaStreamSynchronize(g_stream));
+    return LFM_OK;
+}
+
+// Page-lock / unlock caller-owned host memory (cudaHostRegister) so that the copies of a
+// long-lived buffer (the model's numpy arrays across fit_partial calls) run at PCIe speed.
+extern "C" int lfm_pin_host(void* ptr, int64_t bytes) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (!ptr || bytes <= 0) return fail(LFM_ERR_ARG, "bad host range");
+    int rc = ensure_init();
+    if (rc != LFM_OK) return rc;
+    cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return LFM_OK; }
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(LFM_ERR_CUDA, "cudaHostRegister failed: %s", cudaGetErrorString(e)); }
+    return LFM_OK;
+}
+extern "C" int lfm_unpin_host(void* ptr) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (!ptr || !g_init) return LFM_OK;
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) cudaGetLastError();  // not registered / context gone: nothing to undo
     return LFM_OK;
 }
 
@@ -894,7 +1011,10 @@ extern "C" int lfm_plan_set_global_items(lfm_plan* p, int32_t n_items_global) {
         double fl = floor((double)((n_items_global - 1) / s));
         st.table[s] = (p->loss == LOSS_KOS) ? log(fl) : log(fl > 1.0 ? fl : 1.0);
     }
+    st.table_f.assign(st.table.begin(), st.table.end());
     CU(cudaMemcpyAsync((void*)st.a.loss_table, st.table.data(), sizeof(double) * st.table.size(),
+                       cudaMemcpyHostToDevice, g_stream));
+    CU(cudaMemcpyAsync((void*)st.a.loss_table_f, st.table_f.data(), sizeof(float) * st.table_f.size(),
                        cudaMemcpyHostToDevice, g_stream));
     CU(cudaStreamSynchronize(g_stream));
     return LFM_OK;

@@ -273,7 +273,7 @@ cudaError_t lfm_launch_predict_ranks(const DevCsr& itf, const DevCsr& usf, const
 }
 
 // exported for the host layer: number of floats predict_ranks needs in `scratch`
-extern "C" size_t lfm_ranks_scratch_floats(int n_items, int d, int test_rows) {
+size_t lfm_ranks_scratch_floats(int n_items, int d, int test_rows) {
     return (size_t)n_items * (d + 1) + (size_t)test_rows + 4;
 }
 

@@ -18,6 +18,8 @@ editing the arrays between calls keep working.
 """
 from __future__ import print_function
 
+import warnings
+
 import numpy as np
 import scipy.sparse as sp
 
@@ -37,6 +39,11 @@ _PARAMS = ("loss", "learning_schedule", "no_components", "learning_rate", "k", "
            "epsilon", "max_sampled", "item_alpha", "user_alpha", "random_state")
 
 
+def _abi_model_arrays():
+    from ._abi import _MODEL_ARRAYS
+    return _MODEL_ARRAYS
+
+
 def _as_float32(mat):
     return mat if mat.dtype == CYTHON_DTYPE else mat.astype(CYTHON_DTYPE)
 
@@ -48,6 +55,55 @@ def _is_identity(csr):
             and np.array_equal(csr.indptr, np.arange(n + 1, dtype=csr.indptr.dtype))
             and np.array_equal(csr.indices, np.arange(n, dtype=csr.indices.dtype))
             and np.array_equiv(csr.data, 1.0))
+
+
+def _sample(arr):
+    """A strided sample of a 1-D array (at most ~4096 elements) used to notice in-place edits."""
+    if arr is None:
+        return None
+    return np.array(arr[::max(1, len(arr) // 4096)])
+
+
+class _ResidentCache(object):
+    """What one throughput-mode ``fit_partial`` call leaves behind for the next one: the resident
+    plan (interactions, feature matrices and the membership bitmap / CSR stay in HBM) and the
+    page-locked registration of the model's state arrays.  A later call reuses it when it is given
+    the same input buffers (identity of the COO / feature / weight arrays, their sizes, and a
+    strided sample of their contents) and the same hyper-parameters; anything else rebuilds it."""
+
+    def __init__(self, model, interactions, user_features, item_features, sample_weight):
+        self.hyper = model._hyper_key()
+        self.shape = interactions.shape
+        self.bufs = [interactions.row, interactions.col, interactions.data]
+        self.objs = (user_features, item_features, sample_weight)
+        for m in self.objs:
+            if m is not None:
+                self.bufs.append(m.data)
+        self.samples = [_sample(b) for b in self.bufs]
+        self.plan = None
+        self.pins = None
+        self.features = None            # (user_features, item_features) CSR float32 as uploaded
+        self.sample_weight_data = None
+
+    def matches(self, model, interactions, user_features, item_features, sample_weight):
+        if self.plan is None or self.hyper != model._hyper_key() or self.shape != interactions.shape:
+            return False
+        given = (user_features, item_features, sample_weight)
+        if any(a is not b for a, b in zip(given, self.objs)):
+            return False
+        bufs = [interactions.row, interactions.col, interactions.data] + \
+               [m.data for m in given if m is not None]
+        if len(bufs) != len(self.bufs) or any(a is not b for a, b in zip(bufs, self.bufs)):
+            return False
+        return all(np.array_equal(_sample(b), smp) for b, smp in zip(bufs, self.samples))
+
+    def close(self):
+        if self.plan is not None:
+            self.plan.close()
+            self.plan = None
+        if self.pins is not None:
+            self.pins.release()
+            self.pins = None
 
 
 class LightFM(object):
@@ -105,6 +161,38 @@ class LightFM(object):
     def _reset_state(self):
         for name in _STATE:
             setattr(self, name, None)
+        # the resident cache is keyed on the INPUT buffers and survives fit(): the state arrays are
+        # uploaded at every call anyway
+        self.__dict__.setdefault("_resident_cache", None)
+
+    def release_device(self):
+        """Free what throughput-mode training keeps on the GPU between ``fit_partial`` calls
+        (the resident plan) and un-pin the state arrays.  Training afterwards re-uploads."""
+        cache = self.__dict__.get("_resident_cache")
+        if cache is not None:
+            cache.close()
+        self.__dict__["_resident_cache"] = None
+
+    def __getstate__(self):
+        # device handles do not pickle; the twelve numpy arrays are the whole model (as in L:)
+        state = dict(self.__dict__)
+        state.pop("_resident_cache", None)
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self.__dict__["_resident_cache"] = None
+
+    def __del__(self):
+        try:
+            self.release_device()
+        except Exception:
+            pass
+
+    def _hyper_key(self):
+        return (self.loss, self.learning_schedule, self.no_components, float(self.learning_rate),
+                self.k, self.n, float(self.rho), float(self.epsilon), int(self.max_sampled),
+                float(self.item_alpha), float(self.user_alpha))
 
     def _check_initialized(self):
         if any(getattr(self, name) is None for name in _STATE):
@@ -247,15 +335,27 @@ class LightFM(object):
                 (interactions.data, (interactions.row.astype(np.int32), interactions.col.astype(np.int32))),
                 shape=interactions.shape)
 
-        sample_weight_data = self._process_sample_weight(interactions, sample_weight)
+        if num_threads < 1:
+            raise ValueError("Number of threads must be 1 or larger.")
+        resident = epochs > 0 and _native.resolves_to_hogwild(num_threads) and self._resident_ok()
+        cache = self.__dict__.get("_resident_cache")
+        given = (user_features, item_features, sample_weight)
+        reuse = (resident and cache is not None and self.item_embeddings is not None
+                 and cache.matches(self, interactions, *given))
 
         n_users, n_items = interactions.shape
-        user_features, item_features = self._construct_feature_matrices(
-            n_users, n_items, user_features, item_features)
-
-        for input_data in (user_features.data, item_features.data, interactions.data,
-                           sample_weight_data):
-            self._check_input_finite(input_data)
+        if reuse:
+            # same buffers as the call that built the plan: the O(nnz) host scans below
+            # (all-ones / finiteness / feature coercion) were done then and are not repeated
+            user_features, item_features = cache.features
+            sample_weight_data = cache.sample_weight_data
+        else:
+            sample_weight_data = self._process_sample_weight(interactions, sample_weight)
+            user_features, item_features = self._construct_feature_matrices(
+                n_users, n_items, user_features, item_features)
+            for input_data in (user_features.data, item_features.data, interactions.data,
+                               sample_weight_data):
+                self._check_input_finite(input_data)
 
         if self.item_embeddings is None:
             self._initialize(self.no_components, item_features.shape[1], user_features.shape[1])
@@ -264,14 +364,23 @@ class LightFM(object):
             raise ValueError("Incorrect number of features in item_features")
         if not user_features.shape[1] == self.user_embeddings.shape[0]:
             raise ValueError("Incorrect number of features in user_features")
-        if num_threads < 1:
-            raise ValueError("Number of threads must be 1 or larger.")
 
-        if epochs > 0 and _native.resolves_to_hogwild(num_threads) and self._resident_ok():
-            self._run_epochs_resident(item_features, user_features, interactions,
+        if resident:
+            if not reuse:
+                self.release_device()
+                cache = _ResidentCache(self, interactions, *given)
+                cache.features = (user_features, item_features)
+                cache.sample_weight_data = sample_weight_data
+                self.__dict__["_resident_cache"] = cache
+            self._run_epochs_resident(cache, item_features, user_features, interactions,
                                       sample_weight_data, num_threads, epochs, verbose)
             return self
 
+        if epochs > 0 and len(interactions.data) > 200000 and not getattr(LightFM, "_warned_replay", False):
+            LightFM._warned_replay = True
+            warnings.warn("lightfm_b200: num_threads=1 selects the deterministic replay mode (one "
+                          "sequential stream, bit-reproducible, slow); pass num_threads > 1 for the "
+                          "GPU throughput kernels.", RuntimeWarning, stacklevel=2)
         for _ in self._progress(epochs, verbose=verbose):
             self._run_epoch(item_features, user_features, interactions, sample_weight_data,
                             num_threads, self.loss)
@@ -282,35 +391,31 @@ class LightFM(object):
         # k-OS with n > 32 falls back to replay inside the library; keep the per-epoch path there
         return self.no_components <= 256 and not (self.loss == "warp-kos" and self.n > 32)
 
-    def _run_epochs_resident(self, item_features, user_features, interactions, sample_weight,
+    def _run_epochs_resident(self, cache, item_features, user_features, interactions, sample_weight,
                              num_threads, epochs, verbose):
-        """Throughput mode: upload the problem once, run all epochs on the device
-        (SURVEY 8(f) row 1).  The reference re-builds the positives CSR, re-shuffles on the host
-        and re-crosses the boundary with every array once per epoch (L:668-759); here each epoch
-        consumes one block of ``random_state.randint`` draws (folded into the key of the device-side
-        permutation and of the Philox negative sampler), so the caller's RandomState still
-        advances every epoch.
-        The numpy state arrays are written back once at the end (or before raising)."""
-        pairwise = self.loss in ("warp", "bpr", "warp-kos")
-        kos = self.loss == "warp-kos"
-        # WARP / BPR on the bitmap fast path: the library builds the membership bitmap on the
-        # device straight from the COO arrays, so the COO -> sorted-CSR conversion the reference
-        # repeats every epoch (L:684-686, ~1.3 s of host time at 20 M interactions) is not needed
-        # at all.  Conditions mirror lfm_plan_create's.
-        n_users, n_items = interactions.shape
-        csr_free = (self.loss in ("warp", "bpr") and self.learning_schedule == "adagrad"
-                    and self.item_alpha == 0.0 and self.user_alpha == 0.0
-                    and self.no_components in (16, 32, 64, 128)
-                    and _is_identity(item_features) and _is_identity(user_features)
-                    and n_users * ((n_items + 31) // 32) * 4 <= _native.bitmap_limit())
-        positives = None
-        if pairwise and not csr_free:
-            positives = _native.CSRMatrix(self._positives_lookup(interactions))
-        plan = _native.ResidentPlan(
-            self.loss, _native.CSRMatrix(item_features), _native.CSRMatrix(user_features), positives,
-            interactions.row, None if kos else interactions.col, None if kos else interactions.data,
-            None if kos else sample_weight, self._get_lightfm_data(), self.item_alpha,
-            self.user_alpha, self.k, self.n)
+        """Throughput mode: the problem lives in HBM.  The reference re-builds
+        the positives CSR, re-shuffles on the host and re-crosses the boundary with every array
+        once per epoch (L:668-759).  Here the interactions, features and membership structure are
+        uploaded once per distinct input (``_ResidentCache``), every call uploads the twelve state
+        arrays (the numpy arrays stay authoritative between calls: pickling, resuming and editing
+        them keep working), runs all epochs on the device and writes the state back once.  Each
+        epoch consumes one block of ``random_state.randint`` draws (folded into the key of the
+        device-side permutation and of the Philox negative sampler), so the caller's RandomState
+        still advances every epoch."""
+        state = self._get_lightfm_data()
+        arrays = [getattr(state, n) for n in _abi_model_arrays()]
+        if self.learning_schedule != "adadelta":
+            arrays = [a for n, a in zip(_abi_model_arrays(), arrays) if "momentum" not in n]
+        if cache.pins is None or not cache.pins.holds(arrays):
+            if cache.pins is not None:
+                cache.pins.release()
+            cache.pins = _native.PinnedArrays(arrays)
+        if cache.plan is None:
+            cache.plan = self._make_plan(item_features, user_features, interactions, sample_weight, state)
+        else:
+            cache.plan.upload_model(state)
+        plan = cache.plan
+        finite = True
         try:
             for _ in self._progress(epochs, verbose=verbose):
                 # 625 words: one full Mersenne-Twister block, so get_state()[1] changes every
@@ -319,12 +424,44 @@ class LightFM(object):
                 words = self.random_state.randint(0, np.iinfo(np.int32).max, size=625)
                 seed = int(np.bitwise_xor.reduce(words.astype(np.uint32) * np.uint32(2654435761)))
                 plan.epoch(seed, num_threads=max(2, num_threads))
-                if not plan.all_finite():
+                finite = plan.all_finite()   # the divergence check of L:447-464, on the device
+                if not finite:
                     break
-        finally:
-            plan.download()
-            plan.close()
-        self._check_finite()
+        except Exception:
+            self.release_device()
+            raise
+        plan.download()
+        if not finite:
+            self._check_finite()
+
+    def _make_plan(self, item_features, user_features, interactions, sample_weight, state):
+        pairwise = self.loss in ("warp", "bpr", "warp-kos")
+        kos = self.loss == "warp-kos"
+        # WARP / BPR on the bitmap fast path: the library builds the membership bitmap on the
+        # device straight from the COO arrays, so the COO -> sorted-CSR conversion the reference
+        # repeats every epoch (L:684-686, ~1.3 s of host time at 20 M interactions) is not needed
+        # at all.  Conditions mirror lfm_plan_create's (sizes are the FEATURE matrices' row counts:
+        # negatives are drawn from [0, item_features.shape[0]), L:314-363 allows more rows than items).
+        n_urows, n_irows = user_features.shape[0], item_features.shape[0]
+        csr_free = (self.loss in ("warp", "bpr") and self.learning_schedule == "adagrad"
+                    and self.item_alpha == 0.0 and self.user_alpha == 0.0
+                    and self.no_components in (16, 32, 64, 128)
+                    and _is_identity(item_features) and _is_identity(user_features)
+                    and n_urows * ((n_irows + 31) // 32) * 4 <= _native.bitmap_limit())
+
+        def build(positives):
+            return _native.ResidentPlan(
+                self.loss, _native.CSRMatrix(item_features), _native.CSRMatrix(user_features), positives,
+                interactions.row, None if kos else interactions.col, None if kos else interactions.data,
+                None if kos else sample_weight, state, self.item_alpha, self.user_alpha, self.k, self.n)
+
+        if pairwise and csr_free:
+            try:
+                return build(None)
+            except ValueError:
+                pass  # the library declined the bitmap-only plan: build the sorted CSR after all
+        positives = _native.CSRMatrix(self._positives_lookup(interactions)) if pairwise else None
+        return build(positives)
 
     def _run_epoch(self, item_features, user_features, interactions, sample_weight,
                    num_threads, loss):

@@ -147,6 +147,9 @@ class ShardedTrainer(object):
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        # libfm_cuda defaults to device 0: bind it to this rank's GPU before the plan allocates
+        # anything (raises if the library was already initialised on another device)
+        native.set_device(self.device.index if self.device.index is not None else torch.cuda.current_device())
         coo = interactions.tocoo()
         if coo.dtype != np.float32:
             coo.data = coo.data.astype(np.float32)

@@ -274,3 +274,143 @@ def eval_arrays(arrays, d, train, test, k=10):
         rank_below = np.searchsorted(ns, s[t], side="left")
         aucs.append(float(np.mean(rank_below / neg.sum())))
     return float(np.mean(precs)), float(np.mean(aucs))
+
+
+# ---- tier-B (statistical) parity: scalable planted problems + a subset evaluator ------------
+def planted_clusters(n_users, n_items, nnz, seed, n_clusters=32, p_in=0.8, signed=False):
+    """Interactions with learnable structure at any shape, O(nnz) to generate: users and
+    items belong to one of `n_clusters` groups; a user draws an item from its own group with
+    probability `p_in` (popularity-skewed inside the group), else from the whole catalogue.
+    User activity ~ r^1.5 and item popularity ~ r^2 as in SURVEY 8(d)."""
+    rng = np.random.default_rng(seed)
+    ucl = rng.integers(0, n_clusters, n_users)
+    icl = rng.integers(0, n_clusters, n_items)
+    order = np.argsort(icl, kind="stable")
+    starts = np.searchsorted(icl[order], np.arange(n_clusters + 1))
+    m = int(nnz * 1.5) + 64
+    u = np.floor(n_users * rng.random(m) ** 1.5).astype(np.int64)
+    c = ucl[u]
+    size = (starts[c + 1] - starts[c]).astype(np.int64)
+    inside = (rng.random(m) < p_in) & (size > 0)
+    pos = np.floor(size * rng.random(m) ** 2.0).astype(np.int64)
+    i_in = order[np.minimum(starts[c] + pos, n_items - 1)]
+    i_out = np.floor(n_items * rng.random(m) ** 2.0).astype(np.int64)
+    i = np.where(inside, i_in, i_out)
+    key = np.unique(u * n_items + i)
+    rng.shuffle(key)
+    key = key[:nnz]
+    rows = (key // n_items).astype(np.int32)
+    cols = (key % n_items).astype(np.int32)
+    if signed:
+        data = np.where(rng.random(len(key)) < 0.5, 1.0, -1.0).astype(np.float32)
+    else:
+        data = np.ones(len(key), dtype=np.float32)
+    return sp.coo_matrix((data, (rows, cols)), shape=(n_users, n_items), dtype=np.float32)
+
+
+def eval_subset(arrays, train, test, users, k=10):
+    """Held-out precision@k and AUC (train positives excluded, identity features) of a weight
+    set on the given users, in float64 numpy.  Users without test items are skipped."""
+    users = np.asarray(users)
+    ue = arrays["user_embeddings"][users].astype(np.float64)
+    scores = ue @ arrays["item_embeddings"].astype(np.float64).T
+    scores += arrays["user_biases"][users].astype(np.float64)[:, None]
+    scores += arrays["item_biases"].astype(np.float64)[None, :]
+    tr, te = train.tocsr(), test.tocsr()
+    n_items = scores.shape[1]
+    precs, aucs = [], []
+    for j, u in enumerate(users):
+        t = te.indices[te.indptr[u]:te.indptr[u + 1]]
+        if len(t) == 0:
+            continue
+        s = scores[j]
+        tpos = tr.indices[tr.indptr[u]:tr.indptr[u + 1]]
+        ts = s[t].copy()
+        s[tpos] = -np.inf                                  # never recommended
+        top = np.argpartition(-s, k)[:k]
+        precs.append(len(np.intersect1d(top, t)) / k)
+        nn = n_items - len(np.union1d(tpos, t))            # negatives: neither train nor test
+        if nn <= 0:
+            continue
+        s[tpos] = np.inf                                   # ... and never counted as "below"
+        below = (s[None, :] < ts[:, None]).sum(axis=1) - (ts[None, :] < ts[:, None]).sum(axis=1)
+        aucs.append(float(np.mean(below / nn)))
+    return float(np.mean(precs)), float(np.mean(aucs))
+
+
+def data_digest(inter):
+    """Short fingerprint of a COO matrix (generator drift between hosts would change it)."""
+    import hashlib
+    h = hashlib.sha256()
+    for a in (inter.row, inter.col, inter.data):
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()[:16]
+
+
+# The tier-B problem set (SURVEY 8(c) tier B; VERDICT r1 item 1a).  Shared by the generator of
+# tests/golden/tierb_bands.json (run where the real reference is built) and the GPU tests.
+TIERB = {
+    # C1 shape, 10 epochs, d=16 (SURVEY's own tier-B setting)
+    "c1_warp": dict(shape=(943, 1682), nnz=100_000, clusters=8, loss="warp", d=16, epochs=10),
+    "c1_bpr": dict(shape=(943, 1682), nnz=100_000, clusters=8, loss="bpr", d=16, epochs=10),
+    "c1_logistic": dict(shape=(943, 1682), nnz=100_000, clusters=8, loss="logistic", d=16, epochs=10,
+                        signed=True),
+    "c1_kos": dict(shape=(943, 1682), nnz=100_000, clusters=8, loss="warp-kos", d=16, epochs=10),
+    # C2 shape (138 493 x 26 744), 2.5 M interactions: a full wave of slots in flight on a B200
+    "c2_warp": dict(shape=(138_493, 26_744), nnz=2_500_000, clusters=64, loss="warp", d=64, epochs=3),
+    # (BPR / logistic take small steps: at lr 0.05 three epochs of ~14 interactions per user leave the
+    #  model at chance, so these two run 5 epochs at lr 0.2, where the reference reaches AUC ~0.88-0.90)
+    "c2_bpr": dict(shape=(138_493, 26_744), nnz=2_500_000, clusters=64, loss="bpr", d=64, epochs=5, lr=0.2),
+    "c2_logistic": dict(shape=(138_493, 26_744), nnz=2_500_000, clusters=64, loss="logistic", d=32,
+                        epochs=5, lr=0.2, signed=True),
+    "c2_kos": dict(shape=(138_493, 26_744), nnz=2_500_000, clusters=64, loss="warp-kos", d=64, epochs=2),
+}
+TIERB_SEEDS = (0, 1, 2, 3, 4)
+
+
+_TIERB_CACHE = {}
+
+
+def tierb_problem(name):
+    """(fit matrix, positives-only train for exclusion, test, eval users) of one tier-B case."""
+    key = (TIERB[name]["shape"], TIERB[name]["nnz"], bool(TIERB[name].get("signed")))
+    if key not in _TIERB_CACHE:
+        _TIERB_CACHE[key] = _tierb_problem(name)
+    return _TIERB_CACHE[key]
+
+
+def _tierb_problem(name):
+    cfg = TIERB[name]
+    n_users, n_items = cfg["shape"]
+    base = (cfg["shape"], cfg["nnz"], cfg["clusters"])
+    if base not in _TIERB_CACHE:
+        full = planted_clusters(n_users, n_items, cfg["nnz"], seed=11, n_clusters=cfg["clusters"])
+        _TIERB_CACHE[base] = split(full, 7)
+    train, test = _TIERB_CACHE[base]
+    if cfg.get("signed"):
+        # logistic needs both classes: add as many uniformly drawn explicit negatives as positives
+        rng = np.random.default_rng(3)
+        nr = rng.integers(0, n_users, train.nnz).astype(np.int32)
+        nc = rng.integers(0, n_items, train.nnz).astype(np.int32)
+        fit = sp.coo_matrix((np.concatenate([train.data, -np.ones(train.nnz, np.float32)]),
+                             (np.concatenate([train.row, nr]), np.concatenate([train.col, nc]))),
+                            shape=train.shape)
+    else:
+        fit = train
+    te = test.tocsr()
+    has = np.flatnonzero(np.diff(te.indptr) > 0)
+    rng = np.random.default_rng(5)
+    users = np.sort(rng.choice(has, size=min(1500, len(has)), replace=False))
+    return fit, train, test, users
+
+
+def tierb_fit(api, name, seed, num_threads):
+    """Train one tier-B case through `api`'s native-module surface; returns the weight arrays."""
+    cfg = TIERB[name]
+    fit, _, _, _ = tierb_problem(name)
+    hp = Hyper(d=cfg["d"], lr=cfg.get("lr", 0.05))
+    rs = np.random.RandomState(seed)
+    arr = init_arrays(rs, fit.shape[1], fit.shape[0], cfg["d"])
+    for _ in range(cfg["epochs"]):
+        run_epoch(api, cfg["loss"], fit, arr, hp, rs, num_threads=num_threads)
+    return arr

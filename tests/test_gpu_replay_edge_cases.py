@@ -1,18 +1,15 @@
 """GPU: replay mode on the semantic edge cases for which the oracle is pinned to the real reference
 on the CPU (tests/test_oracle_golden.py, second half).
 
-Written after this round's GPU budget was spent, so they have not run on hardware yet; they are
-non-strict xfail so that an unexpected failure is reported (XFAIL) without hiding the rest of the
-suite behind `-x`, and a pass shows up as XPASS.  Promote to plain tests once seen green."""
+All twelve passed on the B200 in the round-1 driver run (then still marked xfail: 12 XPASS in
+GPUTEST_r01.json); they are plain tests now."""
 import numpy as np
 import pytest
 import scipy.sparse as sp
 
 import helpers as H
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(reason="not yet run on hardware (GPU budget spent); see module docstring",
-                                strict=False)]
+pytestmark = pytest.mark.gpu
 
 
 def _both(loss, inter, d=8, epochs=2, sw=None, exact=None, **hpkw):

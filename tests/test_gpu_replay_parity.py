@@ -114,3 +114,52 @@ def test_regularize_trigger_mid_epoch_matches_oracle():
         outs.append(arr)
     for k in H.MODEL_ARRAYS:
         assert np.array_equal(outs[0][k], outs[1][k], equal_nan=True), k
+
+
+# ---- SURVEY 8(c) tier A1 at the BASELINE widths: slices of C2 / C3 / C5 ----------------------
+# d = 64 and d = 128 take the KMAX register-prefetch path of warp_update (k = 2 and 4 components
+# per lane); C3's [I | tags] item features at d = 128 take the general CSR path.
+
+def _slice_fit(api, loss, inter, d, itf=None, sw=None, epochs=1, **hpkw):
+    hp = H.Hyper(d=d, **hpkw)
+    rs = np.random.RandomState(21)
+    nif = itf.shape[1] if itf is not None else inter.shape[1]
+    arr = H.init_arrays(rs, nif, inter.shape[0], d)
+    for _ in range(epochs):
+        H.run_epoch(api, loss, inter, arr, hp, rs, item_features=itf, sample_weight=sw, num_threads=1)
+    return arr
+
+
+@pytest.mark.parametrize("d", (64, 128))
+def test_c2_slice_warp_replay_bit_equal(d):
+    """C2 slice: 60 k interactions of the 138 493 x 26 744 problem's generator at 1/10 scale."""
+    cu, orc = H.cuda_native(), H.oracle_native()
+    inter = H.synthetic_interactions(13_849, 2_674, 60_000, 2)
+    a, b = _slice_fit(orc, "warp", inter, d), _slice_fit(cu, "warp", inter, d)
+    _compare(b, a, H.MODEL_ARRAYS, exact=True)
+
+
+def test_c2_slice_kos_replay_bit_equal():
+    cu, orc = H.cuda_native(), H.oracle_native()
+    inter = H.synthetic_interactions(13_849, 2_674, 40_000, 4)
+    a, b = _slice_fit(orc, "warp-kos", inter, 64), _slice_fit(cu, "warp-kos", inter, 64)
+    _compare(b, a, H.MODEL_ARRAYS, exact=True)
+
+
+def test_c3_slice_tag_features_d128_replay_bit_equal():
+    """C3 slice: item features = [I | 1000 tags] (8 Zipf tags per item, rows L1-normalised), d=128."""
+    cu, orc = H.cuda_native(), H.oracle_native()
+    inter = H.synthetic_interactions(6_000, 2_674, 30_000, 3)
+    itf = H.tag_features(2_674, 1000, 8, 3)
+    a, b = _slice_fit(orc, "warp", inter, 128, itf=itf), _slice_fit(cu, "warp", inter, 128, itf=itf)
+    _compare(b, a, H.MODEL_ARRAYS, exact=True)
+
+
+def test_c5_slice_weighted_logistic_d32_replay():
+    """C5 slice: explicit +-1 feedback with sample_weight ~ U(0.5, 1.5), logistic, d=32."""
+    cu, orc = H.cuda_native(), H.oracle_native()
+    inter = H.synthetic_interactions(20_000, 2_000, 80_000, 5, signed=True)
+    sw = (0.5 + np.random.default_rng(5).random(inter.nnz)).astype(np.float32)
+    a = _slice_fit(orc, "logistic", inter, 32, sw=sw)
+    b = _slice_fit(cu, "logistic", inter, 32, sw=sw)
+    _compare(b, a, H.MODEL_ARRAYS, exact=False)   # device exp() in the sigmoid: <= 1e-5 relative

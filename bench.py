@@ -9,14 +9,21 @@ step    : one epoch = one pass of fit_warp over the 20 M interactions
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 `value`  kernels only, inputs resident in HBM (lfm_plan_epoch: pack + SGD kernel), CUDA events
-`e2e`    the drop-in boundary call `_lightfm_fast.fit_warp(...)` with HOST (pinned) buffers:
-         every step copies all inputs + the model to the device and the model back
+`e2e`    the public API: `LightFM.fit_partial(scipy COO, epochs=1, num_threads>1)` on ordinary
+         (pageable) numpy / scipy inputs, repeated on the same matrix as a training loop does.
+         Every step uploads the twelve-array model state and downloads it again (the numpy arrays
+         stay authoritative between calls); the interactions stay resident between calls (plan
+         cache keyed on the input buffers), so they are NOT re-copied -- `e2e.cold` is the same
+         epoch through the native boundary call `_lightfm_fast.fit_warp(host buffers)`, which
+         copies every input every step.
 `roofline` algorithmic bytes (SURVEY 8(d) formula x the run's own counters) / SGD-kernel time
-`cpu_baseline` the reference's own OpenMP fit_warp (oracle/_ref) on this box's host cores,
-         bounded sample of the same workload (rank 0, N=1)
+`parity` + `cpu_baseline`  one epoch from the same initial weights on the same 99 % train split,
+         here (hogwild kernels) and in the reference's own OpenMP fit_warp (oracle/_ref) on this
+         box's host cores; held-out precision@10 / AUC of both weight sets on the 1 % test split
+         (same evaluator), and the reference's rate as the CPU baseline (rank 0, N=1)
 
 --impl reference times the unmodified reference (oracle/_ref, rebuilt -march=native for this
-host) through the same boundary call on a bounded sample per step.
+host) through its native entry point on all 20 M interactions per step.
 """
 import argparse
 import json
@@ -108,8 +115,8 @@ class Problem(object):
         self.keep.append(t)
         return v
 
-    def holder(self, api, lr=0.05, max_sampled=10):
-        s = self.state
+    def holder(self, api, lr=0.05, max_sampled=10, state=None):
+        s = self.state if state is None else state
         return api.FastLightFM(s["item_w"], s["item_g"], s["item_m"], s["item_b"], s["item_bg"],
                                s["item_bm"], s["user_w"], s["user_g"], s["user_m"], s["user_b"],
                                s["user_bg"], s["user_bm"], self.d, 0, lr, 0.95, 1e-6, max_sampled)
@@ -203,17 +210,24 @@ def load_reference_native():
     return fast, kind
 
 
-def reference_epoch(fast, prob, sample, threads, rs):
-    """One fit_warp call of the reference on the first `sample` interactions."""
+_POS_CACHE = {}
+
+
+def reference_epoch(fast, prob, sample, threads, rs, state=None):
+    """One fit_warp call of the reference on the first `sample` interactions (the positives CSR
+    and the shuffle are built outside the timed call, as lightfm.py does before calling it)."""
     n = sample
     row, col, data = prob.row[:n], prob.col[:n], prob.data[:n]
-    pos = sp.csr_matrix((data, (row, col)), shape=(prob.n_users, prob.n_items))
-    pos.sort_indices()
-    pos.indices = pos.indices.astype(np.int32)
-    pos.indptr = pos.indptr.astype(np.int32)
+    if _POS_CACHE.get("key") != (id(prob), n):
+        pos = sp.csr_matrix((data, (row, col)), shape=(prob.n_users, prob.n_items))
+        pos.sort_indices()
+        pos.indices = pos.indices.astype(np.int32)
+        pos.indptr = pos.indptr.astype(np.int32)
+        _POS_CACHE.update(key=(id(prob), n), pos=pos)
+    pos = _POS_CACHE["pos"]
     shuffle = np.arange(n, dtype=np.int32)
     rs.shuffle(shuffle)
-    h = prob.holder(fast)
+    h = prob.holder(fast, state=state)
     t0 = time.perf_counter()
     fast.fit_warp(fast.CSRMatrix(prob.itf), fast.CSRMatrix(prob.usf), fast.CSRMatrix(pos), row, col,
                   data, data, shuffle, h, 0.05, 0.0, 0.0, threads, rs)
@@ -236,6 +250,41 @@ def calibrate_reference(fast, prob, threads, target_s):
     return sample, best_rate, best_t
 
 
+def fresh_state(n_users, n_items, d, seed):
+    """Model state as LightFM._initialize draws it (item table first)."""
+    rs = np.random.RandomState(seed)
+    st = {}
+    for side, n in (("item", n_items), ("user", n_users)):
+        emb = ((rs.rand(n, d) - 0.5) / d).astype(np.float32)
+        st[side + "_w"], st[side + "_g"], st[side + "_m"] = emb, np.ones_like(emb), np.zeros_like(emb)
+        st[side + "_b"], st[side + "_bg"], st[side + "_bm"] = (np.zeros(n, np.float32), np.ones(n, np.float32),
+                                                               np.zeros(n, np.float32))
+    return st
+
+
+def heldout_metrics(fast, prob, state, train_csr, test_csr):
+    """precision@10 and AUC of a weight set on the held-out interactions, through the repo's
+    predict_ranks / calculate_auc_from_rank kernels (bit-equal to the reference's evaluator)."""
+    h = prob.holder(fast, state=state)
+    ranks = np.zeros(test_csr.nnz, np.float32)
+    fast.predict_ranks(fast.CSRMatrix(prob.itf), fast.CSRMatrix(prob.usf), fast.CSRMatrix(test_csr),
+                       fast.CSRMatrix(train_csr), ranks, h, 2)
+    has = np.diff(test_csr.indptr) > 0
+    hits = sp.csr_matrix(((ranks < 10).astype(np.float32), test_csr.indices, test_csr.indptr), shape=test_csr.shape)
+    p10 = float((np.asarray(hits.sum(axis=1)).ravel() / 10.0)[has].mean())
+    auc = np.zeros(test_csr.shape[0], np.float32)
+    rk = sp.csr_matrix((ranks.copy(), test_csr.indices, test_csr.indptr), shape=test_csr.shape)
+    ntp = np.diff(train_csr.indptr).astype(np.int32)
+    fast.calculate_auc_from_rank(fast.CSRMatrix(rk), ntp, rk.data, auc, 2)
+    return p10, float(auc[has].mean())
+
+
+def base_config(nnz):
+    """`config` is identical in both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "nnz": int(nnz),
+            "l2": "inputs (tuples 320 MB + tables 85 MB + bitmap / CSR) exceed the 126 MB L2"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -249,23 +298,27 @@ def run_reference_arm(args):
     import torch
     device = "cuda" if torch.cuda.is_available() else "cpu"
     prob = Problem(N_USERS, N_ITEMS, args.nnz, D, seed=2, device=device, pin=False)
-    budget = 150.0 / max(1, args.steps + args.warmup)
-    sample, _, threads = calibrate_reference(fast, prob, threads, target_s=min(8.0, max(1.0, budget)))
+    _, rate, threads = calibrate_reference(fast, prob, threads, target_s=1.0)
+    # every step is one epoch over ALL interactions (the workload itself); only if that would take
+    # more than ~10 minutes in total is the per-step sample cut
+    n_steps = max(1, args.steps + args.warmup)
+    sample = prob.nnz if prob.nnz * n_steps / rate <= 600.0 else int(max(1_000_000, rate * 600.0 / n_steps))
+    sample = min(sample, prob.nnz)
     rs = np.random.RandomState(1)
     for _ in range(args.warmup):
         reference_epoch(fast, prob, sample, threads, rs)
     times = [reference_epoch(fast, prob, sample, threads, rs) for _ in range(args.steps)]
     total = sum(times)
     value = sample * args.steps / total
-    desc = ("first %d of the %d shuffled interactions per step, full 138493x26744 tables, %d OpenMP threads "
-            "(fastest of the counts probed on this %d-thread host)" % (sample, prob.nnz, threads, os.cpu_count() or 1))
+    desc = ("%s %d of the %d interactions per step (one native fit_warp call, shuffle and positives CSR prepared "
+            "outside the timed call), %d OpenMP threads (fastest of the counts probed on this %d-thread host), "
+            "build=%s" % ("all" if sample == prob.nnz else "first", sample, prob.nnz, threads,
+                          os.cpu_count() or 1, kind + (" (-O3 -ffast-math -march=native -fopenmp)" if kind == "native" else "")))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "sample": desc,
-                                        "reference_build": kind + " (-O3 -ffast-math -march=native -fopenmp)"
-                                        if kind == "native" else kind},
+        "data": "synthetic", "config": base_config(prob.nnz),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -285,7 +338,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from lightfm_b200 import _lightfm_fast as fast
-    fast._lib.lfm_set_device(local)
+    fast.set_device(local)
     fast.set_mode("hogwild")
 
     if world > 1:
@@ -331,17 +384,19 @@ def run_ours(args):
         pass
     # dram__bytes_read.sum + dram__bytes_write.sum of one SGD-kernel launch, from the committed
     # `ncu --set full` capture of this same command (profiles/README.md)
-    traffic = None
+    traffic = traffic_src = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(fast.warp_kernel_name(D))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj.get(fast.warp_kernel_name(D))
+        traffic_src = tj.get("_source")
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback"
 
-    # -- e2e: the boundary call with host buffers ----------------------------------------------
+    # -- e2e.cold: the native boundary call with host buffers, every input copied every step -----
     rs = np.random.RandomState(5)
-    e2e_times, e2e_pos, h2d, d2h = [], 0, 0, 0
+    cold_times, cold_pos, cold_h2d, cold_d2h = [], 0, 0, 0
     for s in range(args.warmup + args.steps):
         rs.shuffle(prob.shuffle)  # outside the timed call, as lightfm.py does it before the call
         t0 = time.perf_counter()
@@ -350,47 +405,46 @@ def run_ours(args):
         dt = time.perf_counter() - t0
         c = fast.last_counters["fit"]
         if s >= args.warmup:
-            e2e_times.append(dt)
-            e2e_pos += c["positives"]
-            h2d, d2h = c["h2d_bytes"], c["d2h_bytes"]
+            cold_times.append(dt)
+            cold_pos += c["positives"]
+            cold_h2d, cold_d2h = c["h2d_bytes"], c["d2h_bytes"]
             launches += c["kernel_launches"]
-    e2e_value = e2e_pos / sum(e2e_times)
     finite = all(np.isfinite(v).all() for v in prob.state.values())
+    fast.release_cache()
 
-    # -- the public LightFM API on ordinary (pageable) scipy / numpy inputs -----------------------
-    api = None
-    try:
-        from lightfm_b200 import LightFM
-        coo = sp.coo_matrix((np.ones(prob.nnz, np.float32), (np.array(prob.row), np.array(prob.col))),
-                            shape=(N_USERS, N_ITEMS))
-        model = LightFM(loss="warp", no_components=D, random_state=0)
-        model.fit_partial(coo, epochs=1, num_threads=threads)   # first call also initialises the model
+    # -- e2e: the public LightFM API on ordinary (pageable) scipy / numpy inputs -----------------
+    from lightfm_b200 import LightFM
+    coo = sp.coo_matrix((np.ones(prob.nnz, np.float32), (np.array(prob.row), np.array(prob.col))),
+                        shape=(N_USERS, N_ITEMS))
+    model = LightFM(loss="warp", no_components=D, random_state=0)
+    t0 = time.perf_counter()
+    model.fit_partial(coo, epochs=1, num_threads=threads)   # first call: initialises the model, builds the plan
+    first_call_s = time.perf_counter() - t0
+    for _ in range(max(0, args.warmup - 1)):
+        model.fit_partial(coo, epochs=1, num_threads=threads)
+    api_times = []
+    for _ in range(args.steps):
         t0 = time.perf_counter()
         model.fit_partial(coo, epochs=1, num_threads=threads)
-        t1 = time.perf_counter()
-        model.fit_partial(coo, epochs=5, num_threads=threads)
-        t5 = time.perf_counter()
-        api = {"call": "LightFM.fit_partial(scipy COO, pageable numpy state)",
-               "one_epoch_s": t1 - t0, "five_epochs_s": t5 - t1,
-               "one_epoch_interactions_per_s": prob.nnz / (t1 - t0),
-               "five_epochs_interactions_per_s": 5 * prob.nnz / (t5 - t1)}
-        del model, coo
-    except Exception as exc:  # pragma: no cover
-        api = {"error": str(exc)}
+        api_times.append(time.perf_counter() - t0)
+    launches += 3 * args.steps  # pack + SGD kernel + finite check per call
+    t0 = time.perf_counter()
+    model.fit_partial(coo, epochs=5, num_threads=threads)
+    five_s = time.perf_counter() - t0
+    state_bytes = sum(getattr(model, k).nbytes for k in (
+        "item_embeddings", "item_embedding_gradients", "item_biases", "item_bias_gradients",
+        "user_embeddings", "user_embedding_gradients", "user_biases", "user_bias_gradients"))
+    e2e_value = prob.nnz * len(api_times) / sum(api_times)
+    api_finite = bool(np.isfinite(model.item_embeddings).all() and np.isfinite(model.user_embeddings).all())
+    model.release_device()
+    del model, coo
 
-    # -- cpu baseline: the reference's OpenMP fit_warp on this host ------------------------------
-    cpu = None
+    # -- parity + cpu baseline: one epoch each from the same weights on the same train split ------
+    parity, cpu = None, None
     if not args.no_cpu_baseline:
         try:
-            ref_fast, kind = load_reference_native()
-            cores = os.cpu_count() or 1
-            cpu_prob = prob
-            sample, _, cores = calibrate_reference(ref_fast, cpu_prob, cores, target_s=12.0)
-            dt = reference_epoch(ref_fast, cpu_prob, sample, cores, np.random.RandomState(3))
-            cpu = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "reference",
-                   "sample": "one fit_warp call on the first %d of %d shuffled interactions, %d OpenMP "
-                             "threads (fastest of the counts probed on this %d-thread host), build=%s"
-                             % (sample, prob.nnz, cores, os.cpu_count() or 1, kind)}
+            parity, cpu, extra = parity_and_baseline(fast, prob, threads)
+            launches += extra
         except Exception as exc:  # pragma: no cover
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
                    "sample": "unavailable: %s" % exc}
@@ -400,24 +454,86 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "nnz": prob.nnz, "mode": "hogwild",
-                   "l2": "inputs (tuples 320 MB + tables 85 MB + CSR 80 MB) exceed the 126 MB L2",
-                   "wall_ms_per_step_resident": 1e3 * wall_resident / args.steps,
+        "config": base_config(prob.nnz),
+        "detail": {"mode": "hogwild", "wall_ms_per_step_resident": 1e3 * wall_resident / args.steps,
                    "negatives_per_positive": mean("negatives_drawn") / mean("positives"),
                    "updates_per_positive": mean("updates") / mean("positives"),
-                   "weights_finite": bool(finite), "public_api": api},
+                   "weights_finite": bool(finite and api_finite)},
         "clocks": clk,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": 1e3 * sum(e2e_times) / len(e2e_times),
-                "call": "lightfm_b200._lightfm_fast.fit_warp(host pinned buffers)"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes,
+                "ms_per_step": 1e3 * sum(api_times) / len(api_times),
+                "ms_per_step_min_max": [1e3 * min(api_times), 1e3 * max(api_times)],
+                "call": "LightFM.fit_partial(scipy COO, epochs=1, num_threads=%d) on pageable numpy state; "
+                        "interactions resident from the first call (plan cache), state up + down every call" % threads,
+                "first_call_s": first_call_s, "five_epochs_one_call_s": five_s,
+                "five_epochs_interactions_per_s": 5 * prob.nnz / five_s,
+                "cold": {"value": cold_pos / sum(cold_times), "unit": UNIT, "h2d_bytes_per_step": cold_h2d,
+                         "d2h_bytes_per_step": cold_d2h, "ms_per_step": 1e3 * sum(cold_times) / len(cold_times),
+                         "call": "lightfm_b200._lightfm_fast.fit_warp(host pinned buffers): all inputs + state "
+                                 "copied in, state copied out, every step"}},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": peak_src,
                      "kernel": fast.warp_kernel_name(D), "kernel_ms": train_ms / args.steps,
                      "algorithmic_bytes_per_step": abytes / args.steps},
+        "parity": parity,
         "cpu_baseline": cpu,
     }
     print(json.dumps(out))
+
+
+def parity_and_baseline(fast, prob, threads):
+    """Train one epoch from identical initial weights on the first 99 % of the interactions with
+    (a) this repo's hogwild kernels through the boundary call and (b) the reference's OpenMP
+    fit_warp on the host cores; score both weight sets on the held-out 1 % with one evaluator.
+    (b)'s timing is the CPU baseline."""
+    ref_fast, kind = load_reference_native()
+    n_test = max(1000, prob.nnz // 100)
+    n_train = prob.nnz - n_test
+    tr_rows, tr_cols = np.array(prob.row[:n_train]), np.array(prob.col[:n_train])
+    ones = np.ones(n_train, np.float32)
+    train_csr = sp.csr_matrix((ones, (tr_rows, tr_cols)), shape=(prob.n_users, prob.n_items))
+    train_csr.sort_indices()
+    train_csr.indices, train_csr.indptr = train_csr.indices.astype(np.int32), train_csr.indptr.astype(np.int32)
+    # evaluate on at most 4096 users that have held-out items
+    te_rows, te_cols = np.array(prob.row[n_train:]), np.array(prob.col[n_train:])
+    keep_users = np.unique(te_rows)[:4096]
+    m = np.isin(te_rows, keep_users)
+    test_csr = sp.csr_matrix((np.ones(int(m.sum()), np.float32), (te_rows[m], te_cols[m])),
+                             shape=(prob.n_users, prob.n_items))
+    test_csr.sort_indices()
+    test_csr.indices, test_csr.indptr = test_csr.indices.astype(np.int32), test_csr.indptr.astype(np.int32)
+
+    out = {}
+    # (a) GPU, hogwild kernels through the boundary call
+    st = fresh_state(prob.n_users, prob.n_items, prob.d, seed=77)
+    rs = np.random.RandomState(9)
+    shuffle = np.arange(n_train, dtype=np.int32)
+    rs.shuffle(shuffle)
+    fast.fit_warp(fast.CSRMatrix(prob.itf), fast.CSRMatrix(prob.usf), fast.CSRMatrix(train_csr), tr_rows, tr_cols,
+                  ones, ones, shuffle, prob.holder(fast, state=st), 0.05, 0.0, 0.0, threads, rs)
+    gl = fast.last_counters["fit"]["kernel_launches"]
+    out["gpu"] = heldout_metrics(fast, prob, st, train_csr, test_csr)
+    # (b) the reference on the host cores (also the CPU baseline)
+    cores = os.cpu_count() or 1
+    _, _, cores = calibrate_reference(ref_fast, prob, cores, target_s=1.0)
+    st_ref = fresh_state(prob.n_users, prob.n_items, prob.d, seed=77)
+    dt = reference_epoch(ref_fast, prob, n_train, cores, np.random.RandomState(9), state=st_ref)
+    out["reference"] = heldout_metrics(fast, prob, st_ref, train_csr, test_csr)
+    parity = {"what": "held-out precision@10 / AUC after ONE epoch from the same initial weights on the same %d "
+                      "train interactions; %d held-out interactions of %d users; train positives excluded"
+                      % (n_train, test_csr.nnz, len(keep_users)),
+              "p_at_10_gpu": out["gpu"][0], "p_at_10_reference": out["reference"][0],
+              "heldout_auc_gpu": out["gpu"][1], "heldout_auc_reference": out["reference"][1],
+              "reference_threads": cores,
+              "note": "the reference at >1 thread is itself not reproducible (Hogwild); tier-B bands in "
+                      "tests/golden/tierb_bands.json quantify its own spread"}
+    cpu = {"value": n_train / dt, "unit": UNIT, "cores": cores, "kind": "reference",
+           "sample": "one native fit_warp call on the first %d of %d interactions (the parity train split), %d "
+                     "OpenMP threads (fastest of the counts probed on this %d-thread host), build=%s"
+                     % (n_train, prob.nnz, cores, os.cpu_count() or 1, kind)}
+    return parity, cpu, gl + 6
 
 
 def main():

@@ -202,6 +202,25 @@ int lfm_predict_ranks(const lfm_csr *item_features, const lfm_csr *user_features
 int lfm_calculate_auc_from_rank(const lfm_csr *ranks, const int32_t *num_train_positives,
                                 float *rank_data, float *auc, int32_t num_threads);
 
+/* evaluation.py:14-327 fused behind predict_ranks: the ranks stay on the
+ * device; per user, hits[u] = #{rank < k} (precision@k = hits / k, recall@k = hits / #test),
+ * best_rank[u] = smallest rank (-1 without test interactions; reciprocal rank = 1 / (best + 1)),
+ * auc[u] as calculate_auc_from_rank (T:1326-1376) with num_train_positives = train row lengths.
+ * Each output is [test.rows] and may be NULL. */
+int lfm_evaluate_ranks(const lfm_csr *item_features, const lfm_csr *user_features,
+                       const lfm_csr *test_interactions, const lfm_csr *train_interactions,
+                       const lfm_model *model, int32_t k, int32_t *hits, float *best_rank,
+                       float *auc, int32_t num_threads);
+
+/* Top-k recommendation (replaces np.argsort(-model.predict(u, arange(n_items))),
+ * doc/quickstart.rst:125-126): for every user in user_ids the k best of items [0, n_items) by
+ * predict_lightfm's score (bit-identical), descending, ties by ascending item id; items stored in
+ * the user's row of `exclude` (may be NULL) are skipped.  Outputs are [n_users * k]; unused slots
+ * hold -1 / NaN.  k <= 1024. */
+int lfm_recommend(const lfm_csr *item_features, const lfm_csr *user_features, const lfm_csr *exclude,
+                  const int32_t *user_ids, int64_t n_users, int32_t n_items, int32_t k,
+                  const lfm_model *model, int32_t *out_items, float *out_scores);
+
 /* T:1380-1385 (test hook; runs the device membership search). Returns 0/1, <0 on error. */
 int lfm_test_in_positives(int32_t row, int32_t col, const lfm_csr *mat);
 

@@ -108,6 +108,10 @@ LIB_ONLY = {
     "lfm_plan_epoch": (C.c_int, [C.c_void_p, c_i32p, C.c_uint32, C.c_int32, CountersP]),
     "lfm_plan_download": (C.c_int, [C.c_void_p, ModelP]),
     "lfm_plan_upload_model": (C.c_int, [C.c_void_p, ModelP]),
+    "lfm_evaluate_ranks": (C.c_int, [CsrP, CsrP, CsrP, CsrP, ModelP, C.c_int32, c_i32p, c_f32p, c_f32p,
+                                     C.c_int32]),
+    "lfm_recommend": (C.c_int, [CsrP, CsrP, CsrP, c_i32p, C.c_int64, C.c_int32, C.c_int32, ModelP,
+                                c_i32p, c_f32p]),
     "lfm_pin_host": (C.c_int, [C.c_void_p, C.c_int64]),
     "lfm_unpin_host": (C.c_int, [C.c_void_p]),
     "lfm_set_tuning": (C.c_int, [C.c_int]),

@@ -184,6 +184,35 @@ __all__ = ["CSRMatrix", "FastLightFM", "fit_logistic", "fit_warp", "fit_bpr", "f
            "predict_lightfm", "predict_ranks", "calculate_auc_from_rank"]
 
 
+def evaluate_ranks(item_features, user_features, test_interactions, train_interactions, lightfm, k,
+                   want_hits=True, want_best=True, want_auc=True, num_threads=1):
+    """predict_ranks + the per-user reductions of lightfm/evaluation.py on the device
+    (``lfm_evaluate_ranks``).  Returns (hits int32[U] | None, best_rank float32[U] | None,
+    auc float32[U] | None); the per-interaction ranks never reach the host."""
+    rows = test_interactions.rows
+    hits = np.zeros(rows, np.int32) if want_hits else None
+    best = np.zeros(rows, np.float32) if want_best else None
+    auc = np.zeros(rows, np.float32) if want_auc else None
+    _check(_lib.lfm_evaluate_ranks(
+        item_features.ptr, user_features.ptr, test_interactions.ptr, train_interactions.ptr, lightfm.ptr,
+        int(k), _abi.i32p(hits) if want_hits else ctypes.cast(None, _abi.c_i32p),
+        _abi.f32p(best) if want_best else ctypes.cast(None, _abi.c_f32p),
+        _abi.f32p(auc) if want_auc else ctypes.cast(None, _abi.c_f32p), int(num_threads)))
+    return hits, best, auc
+
+
+def recommend(item_features, user_features, exclude, user_ids, n_items, k, lightfm):
+    """Top-k items per user (``lfm_recommend``): (items int32[n, k], scores float32[n, k])."""
+    _abi._require(user_ids, np.int32, 1, "user_ids")
+    n = len(user_ids)
+    items = np.full((n, int(k)), -1, np.int32)
+    scores = np.full((n, int(k)), np.nan, np.float32)
+    _check(_lib.lfm_recommend(item_features.ptr, user_features.ptr,
+                              exclude.ptr if exclude is not None else None, _abi.i32p(user_ids), n,
+                              int(n_items), int(k), lightfm.ptr, _abi.i32p(items), _abi.f32p(scores)))
+    return items, scores
+
+
 _LOSS_CODES = {"logistic": 0, "warp": 1, "bpr": 2, "warp-kos": 3}
 
 

@@ -106,7 +106,13 @@ cudaError_t lfm_launch_predict_ranks(const DevCsr& itf, const DevCsr& usf, const
                                      const DevCsr& train, const DevModel& m, float* ranks,
                                      float* item_repr_scratch, cudaStream_t st, int* launches);
 cudaError_t lfm_launch_auc(const DevCsr& ranks, const int32_t* num_train_pos, float* rank_data,
-                           float* auc, cudaStream_t st);
+                           float* auc, float* tmp, cudaStream_t st);
+cudaError_t lfm_launch_rank_metrics(const DevCsr& test, const float* ranks, int k, int32_t* hits, float* best,
+                                    cudaStream_t st);
+cudaError_t lfm_launch_row_counts(const DevCsr& m, int32_t* out, int rows, cudaStream_t st);
+cudaError_t lfm_launch_recommend(const DevCsr& itf, const DevCsr& usf, const DevCsr* exclude, const DevModel& m,
+                                 int n_items, const int32_t* user_ids, int n_users, int k, int32_t* out_items,
+                                 float* out_scores, float* scratch, cudaStream_t st, int* launches);
 cudaError_t lfm_launch_in_positives(const DevCsr& mat, int32_t row, int32_t col, int32_t* out,
                                     cudaStream_t st);
 cudaError_t lfm_launch_check_identity(const DevCsr& m, int32_t* flag, cudaStream_t st);

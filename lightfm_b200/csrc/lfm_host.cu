@@ -735,12 +735,144 @@ extern "C" int lfm_calculate_auc_from_rank(const lfm_csr* ranks, const int32_t* 
     if (rc != LFM_OK) return rc;
     rc = upload("auc.auc", (const float*)auc, (size_t)ranks->rows, &d_auc, x);
     if (rc != LFM_OK) return rc;
-    CU(lfm_launch_auc(dr, d_ntp, d_rank, d_auc, g_stream));
+    void* tmp = nullptr;
+    rc = arena_get("auc.tmp", sizeof(float) * (size_t)ranks->nnz, &tmp);
+    if (rc != LFM_OK) return rc;
+    CU(lfm_launch_auc(dr, d_ntp, d_rank, d_auc, (float*)tmp, g_stream));
     rc = download(rank_data, (const float*)d_rank, (size_t)ranks->nnz, x);
     if (rc != LFM_OK) return rc;
     rc = download(auc, (const float*)d_auc, (size_t)ranks->rows, x);
     if (rc != LFM_OK) return rc;
     CU(cudaStreamSynchronize(g_stream));
+    return LFM_OK;
+}
+
+// Fused evaluation (lightfm/evaluation.py:14-327): predict_ranks, then the per-user reductions on
+// the device -- hits[u] = #{rank < k}, best_rank[u] = smallest rank (-1 for users without test
+// interactions), auc[u] as calculate_auc_from_rank computes it (num_train_positives = the train
+// rows' lengths).  Any of the three outputs may be NULL.  The nnz_test ranks never leave the GPU.
+extern "C" int lfm_evaluate_ranks(const lfm_csr* item_features, const lfm_csr* user_features,
+                                  const lfm_csr* test_interactions, const lfm_csr* train_interactions,
+                                  const lfm_model* model, int32_t k, int32_t* hits, float* best_rank,
+                                  float* auc, int32_t num_threads) {
+    (void)num_threads;
+    std::lock_guard<std::mutex> lock(g_mu);
+    g_cur = &g_arena;
+    int rc = check_csr(test_interactions, "test_interactions", false);
+    if (rc != LFM_OK) return rc;
+    rc = check_csr(train_interactions, "train_interactions", false);
+    if (rc != LFM_OK) return rc;
+    if (train_interactions->rows < test_interactions->rows)
+        return fail(LFM_ERR_ARG, "train_interactions has fewer rows than test_interactions");
+    if (k < 0) return fail(LFM_ERR_ARG, "negative k");
+    rc = ensure_init();
+    if (rc != LFM_OK) return rc;
+    Xfer x;
+    DevCsr itf, usf, test, train;
+    DevModel dm;
+    rc = upload_csr("itf", item_features, true, false, &itf, x);
+    if (rc != LFM_OK) return rc;
+    rc = upload_csr("usf", user_features, true, false, &usf, x);
+    if (rc != LFM_OK) return rc;
+    rc = upload_csr("ranks.test", test_interactions, false, false, &test, x);
+    if (rc != LFM_OK) return rc;
+    rc = upload_csr("ranks.train", train_interactions, false, false, &train, x);
+    if (rc != LFM_OK) return rc;
+    rc = upload_model(model, false, &dm, x);
+    if (rc != LFM_OK) return rc;
+    if (itf.rows < test.cols) return fail(LFM_ERR_ARG, "item_features has fewer rows than there are items");
+    if (usf.rows < test.rows) return fail(LFM_ERR_ARG, "user_features has fewer rows than there are users");
+    const size_t nnz = (size_t)test.nnz, rows = (size_t)test.rows;
+    void *p = nullptr, *d_ranks = nullptr, *d_hits = nullptr, *d_best = nullptr, *d_auc = nullptr, *d_ntp = nullptr,
+         *d_tmp = nullptr;
+    rc = arena_get("ranks.out", sizeof(float) * nnz, &d_ranks);
+    if (rc != LFM_OK) return rc;
+    rc = arena_get("ranks.scratch", sizeof(float) * lfm_ranks_scratch_floats(test.cols, dm.d, test.rows), &p);
+    if (rc != LFM_OK) return rc;
+    rc = arena_get("eval.hits", sizeof(int32_t) * rows, &d_hits);
+    if (rc != LFM_OK) return rc;
+    rc = arena_get("eval.best", sizeof(float) * rows, &d_best);
+    if (rc != LFM_OK) return rc;
+    rc = arena_get("eval.auc", sizeof(float) * rows, &d_auc);
+    if (rc != LFM_OK) return rc;
+    rc = arena_get("eval.ntp", sizeof(int32_t) * rows, &d_ntp);
+    if (rc != LFM_OK) return rc;
+    rc = arena_get("auc.tmp", sizeof(float) * nnz, &d_tmp);
+    if (rc != LFM_OK) return rc;
+    CU(cudaMemsetAsync(d_ranks, 0, sizeof(float) * nnz, g_stream));
+    int launches = 0;
+    CU(lfm_launch_predict_ranks(itf, usf, test, train, dm, (float*)d_ranks, (float*)p, g_stream, &launches));
+    if (hits || best_rank) CU(lfm_launch_rank_metrics(test, (const float*)d_ranks, k, (int32_t*)d_hits, (float*)d_best, g_stream));
+    if (auc) {
+        CU(lfm_launch_row_counts(train, (int32_t*)d_ntp, test.rows, g_stream));
+        CU(cudaMemsetAsync(d_auc, 0, sizeof(float) * rows, g_stream));
+        CU(lfm_launch_auc(test, (const int32_t*)d_ntp, (float*)d_ranks, (float*)d_auc, (float*)d_tmp, g_stream));
+    }
+    if (hits) { rc = download(hits, (const int32_t*)d_hits, rows, x); if (rc != LFM_OK) return rc; }
+    if (best_rank) { rc = download(best_rank, (const float*)d_best, rows, x); if (rc != LFM_OK) return rc; }
+    if (auc) { rc = download(auc, (const float*)d_auc, rows, x); if (rc != LFM_OK) return rc; }
+    CU(cudaStreamSynchronize(g_stream));
+    return LFM_OK;
+}
+
+// Top-k recommendation for a batch of users (the reference's documented idiom is
+// np.argsort(-model.predict(user, np.arange(n_items))), doc/quickstart.rst:125-126): scores of all
+// n_items items per user as predict_lightfm computes them (bit-identical), the k best in descending
+// score order (ties: lower item id first), optionally skipping the items stored in `exclude`
+// (the user's row of a train matrix).  out_items / out_scores are [n_users * k]; slots beyond the
+// number of scorable items hold -1 / NaN.  k <= 1024.
+extern "C" int lfm_recommend(const lfm_csr* item_features, const lfm_csr* user_features,
+                             const lfm_csr* exclude, const int32_t* user_ids, int64_t n_users, int32_t n_items,
+                             int32_t k, const lfm_model* model, int32_t* out_items, float* out_scores) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    g_cur = &g_arena;
+    if (n_users < 0 || n_items < 0 || k < 0 || k > 1024) return fail(LFM_ERR_ARG, "bad n_users / n_items / k (k <= 1024)");
+    if (n_users > 0 && (!user_ids || (k > 0 && (!out_items || !out_scores)))) return fail(LFM_ERR_ARG, "null array");
+    if (n_users == 0 || k == 0 || n_items == 0) return LFM_OK;
+    int rc = ensure_init();
+    if (rc != LFM_OK) return rc;
+    Xfer x;
+    DevCsr itf, usf, exc;
+    DevModel dm;
+    rc = upload_csr("itf", item_features, true, false, &itf, x);
+    if (rc != LFM_OK) return rc;
+    rc = upload_csr("usf", user_features, true, false, &usf, x);
+    if (rc != LFM_OK) return rc;
+    if (exclude) {
+        rc = upload_csr("rec.exclude", exclude, false, false, &exc, x);
+        if (rc != LFM_OK) return rc;
+    }
+    rc = upload_model(model, false, &dm, x);
+    if (rc != LFM_OK) return rc;
+    if (itf.rows < n_items) return fail(LFM_ERR_ARG, "item_features has fewer rows than n_items");
+    for (int64_t i = 0; i < n_users; i++)
+        if (user_ids[i] < 0 || user_ids[i] >= usf.rows) return fail(LFM_ERR_ARG, "user id out of range");
+    const int ld = (n_items + 3) & ~3;
+    // users are processed in batches whose score rows fit ~2 GiB of scratch
+    int64_t batch = ((int64_t)2 << 30) / ((int64_t)ld * 4);
+    if (batch < 8) batch = 8;
+    if (batch > n_users) batch = n_users;
+    void *scratch = nullptr, *d_items = nullptr, *d_scores = nullptr;
+    rc = arena_get("rec.scratch", sizeof(float) * ((size_t)ld * (dm.d + 1) + (size_t)batch * ld), &scratch);
+    if (rc != LFM_OK) return rc;
+    rc = arena_get("rec.items", sizeof(int32_t) * (size_t)batch * k, &d_items);
+    if (rc != LFM_OK) return rc;
+    rc = arena_get("rec.scores", sizeof(float) * (size_t)batch * k, &d_scores);
+    if (rc != LFM_OK) return rc;
+    int32_t* d_users = nullptr;
+    rc = upload("rec.users", user_ids, (size_t)n_users, &d_users, x);
+    if (rc != LFM_OK) return rc;
+    for (int64_t b0 = 0; b0 < n_users; b0 += batch) {
+        const int nb = (int)((n_users - b0 < batch) ? (n_users - b0) : batch);
+        int launches = 0;
+        CU(lfm_launch_recommend(itf, usf, exclude ? &exc : nullptr, dm, n_items, d_users + b0, nb, k,
+                                (int32_t*)d_items, (float*)d_scores, (float*)scratch, g_stream, &launches));
+        rc = download(out_items + b0 * k, (const int32_t*)d_items, (size_t)nb * k, x);
+        if (rc != LFM_OK) return rc;
+        rc = download(out_scores + b0 * k, (const float*)d_scores, (size_t)nb * k, x);
+        if (rc != LFM_OK) return rc;
+        CU(cudaStreamSynchronize(g_stream));
+    }
     return LFM_OK;
 }
 

@@ -625,6 +625,74 @@ class LightFM(object):
                               self._get_lightfm_data(), num_threads)
         return ranks
 
+    def _rank_inputs(self, test_interactions, train_interactions, item_features, user_features,
+                     num_threads, check_intersections):
+        """Shared argument handling of predict_rank / evaluate_ranks (L:884-989)."""
+        self._check_initialized()
+        if num_threads < 1:
+            raise ValueError("Number of threads must be 1 or larger.")
+        if check_intersections:
+            self._check_test_train_intersections(test_interactions, train_interactions)
+        n_users, n_items = test_interactions.shape
+        user_features, item_features = self._construct_feature_matrices(
+            n_users, n_items, user_features, item_features)
+        if not item_features.shape[1] == self.item_embeddings.shape[0]:
+            raise ValueError("Incorrect number of features in item_features")
+        if not user_features.shape[1] == self.user_embeddings.shape[0]:
+            raise ValueError("Incorrect number of features in user_features")
+        test_interactions = _as_float32(test_interactions.tocsr())
+        if train_interactions is None:
+            train_interactions = sp.csr_matrix((n_users, n_items), dtype=CYTHON_DTYPE)
+        else:
+            train_interactions = _as_float32(train_interactions.tocsr())
+        return test_interactions, train_interactions, item_features, user_features
+
+    def evaluate_ranks(self, test_interactions, train_interactions=None, k=10, item_features=None,
+                       user_features=None, num_threads=1, check_intersections=True,
+                       hits=True, best_rank=True, auc=True):
+        """``predict_rank`` fused with the reductions of ``lightfm.evaluation``:
+        returns per-user ``(hits, best_rank, auc)`` -- the number of test items ranked below ``k``,
+        the smallest rank (-1 for users without test items) and the AUC exactly as
+        ``evaluation.auc_score`` computes it -- without materialising the per-interaction rank
+        matrix on the host.  Outputs that are not requested come back as ``None``."""
+        test, train, item_features, user_features = self._rank_inputs(
+            test_interactions, train_interactions, item_features, user_features, num_threads,
+            check_intersections)
+        return _native.evaluate_ranks(
+            _native.CSRMatrix(item_features), _native.CSRMatrix(user_features), _native.CSRMatrix(test),
+            _native.CSRMatrix(train), self._get_lightfm_data(), k, want_hits=hits, want_best=best_rank,
+            want_auc=auc, num_threads=num_threads)
+
+    def recommend(self, user_ids, k=10, train_interactions=None, item_features=None, user_features=None,
+                  n_items=None):
+        """Top-``k`` items for each user.  The reference documents
+        ``np.argsort(-model.predict(user_id, np.arange(n_items)))`` (doc/quickstart.rst:125-126);
+        this scores the whole catalogue for a batch of users on the device and returns
+        ``(items, scores)``, both ``[len(user_ids), k]``: the ``k`` best items in descending score
+        order (scores bit-identical to ``predict``; ties by ascending item id), skipping the items
+        the user has in ``train_interactions`` when given.  Unused slots hold ``-1`` / ``nan``."""
+        self._check_initialized()
+        user_ids = np.ascontiguousarray(np.atleast_1d(np.asarray(user_ids)).astype(np.int32))
+        if len(user_ids) and user_ids.min() < 0:
+            raise ValueError("User ids cannot be negative.")
+        if n_items is None:
+            if train_interactions is not None:
+                n_items = train_interactions.shape[1]
+            elif item_features is not None:
+                n_items = item_features.shape[0]
+            else:
+                n_items = self.item_embeddings.shape[0]
+        n_users = int(user_ids.max()) + 1 if len(user_ids) else 0
+        if train_interactions is not None:
+            n_users = max(n_users, train_interactions.shape[0])
+        user_features, item_features = self._construct_feature_matrices(
+            n_users, n_items, user_features, item_features)
+        exclude = None
+        if train_interactions is not None:
+            exclude = _native.CSRMatrix(_as_float32(train_interactions.tocsr()))
+        return _native.recommend(_native.CSRMatrix(item_features), _native.CSRMatrix(user_features),
+                                 exclude, user_ids, n_items, k, self._get_lightfm_data())
+
     # ---- representations / sklearn plumbing -------------------------------------------------
     def get_item_representations(self, features=None):
         """(biases, embeddings) of items, optionally projected through ``features`` (L:991-1018)."""

@@ -34,6 +34,10 @@ OUT = os.path.join(HERE, "_ref")
 REFERENCE = os.environ.get("LFM_REFERENCE_DIR", "/root/reference")
 GCC = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
 
+# the reference's offline test modules (the other three need the network), run UNMODIFIED
+# against the drop-in package by tests/test_gpu_reference_suite.py
+REF_TESTS = ["__init__.py", "test_api.py", "test_evaluation.py", "test_fast_functions.py", "test_data.py"]
+
 PY_FILES = ["__init__.py", "_lightfm_fast.py", "lightfm.py", "evaluation.py",
             "cross_validation.py", "data.py", "version.py"]
 
@@ -107,7 +111,21 @@ def build_from_reference():
         _install_py(os.path.join(tree, "lightfm"), pkg)
         _compile(os.path.join(OUT, "csrc", "_lightfm_fast_openmp.c"), pkg, flags)
     shutil.rmtree(tmp, ignore_errors=True)
+    install_tests()
     print("reference built into", OUT)
+
+
+def install_tests():
+    """Copy the reference's offline test modules into oracle/_ref/tests (git-ignored output)."""
+    src = os.path.join(REFERENCE, "tests")
+    if not os.path.isdir(src):
+        raise RuntimeError("%s not present" % src)
+    dst = os.path.join(OUT, "tests")
+    os.makedirs(dst, exist_ok=True)
+    for f in REF_TESTS:
+        shutil.copy(os.path.join(src, f), os.path.join(dst, f))
+        os.chmod(os.path.join(dst, f), 0o644)
+    return dst
 
 
 def rebuild_native():
@@ -134,5 +152,7 @@ def rebuild_native():
 if __name__ == "__main__":
     if "--native" in sys.argv:
         print(rebuild_native())
+    elif "--tests" in sys.argv:
+        print(install_tests())
     else:
         build_from_reference()

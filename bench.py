@@ -449,6 +449,19 @@ def run_ours(args):
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
                    "sample": "unavailable: %s" % exc}
 
+    # -- C4 on one GPU (the N = 1 point of the strong-scaling curve) -------------------------------
+    c4 = None
+    if not args.no_c4:
+        try:
+            import bench_c4
+            from lightfm_b200 import sharding
+            fast.release_cache()
+            torch.cuda.empty_cache()
+            c4 = bench_c4.run(fast, sharding, dist, 0, 1, torch.device("cuda", local), epochs=2, peak=peak)
+            launches += 3 * 2
+        except Exception as exc:  # pragma: no cover
+            c4 = {"error": "%s: %s" % (type(exc).__name__, exc)}
+
     mean = lambda k: sum(c[k] for c in counters) / len(counters)
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
@@ -479,6 +492,7 @@ def run_ours(args):
                      "algorithmic_bytes_per_step": abytes / args.steps},
         "parity": parity,
         "cpu_baseline": cpu,
+        "c4": c4,
     }
     print(json.dumps(out))
 
@@ -544,6 +558,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     ap.add_argument("--nnz", type=int, default=NNZ, help="debug: smaller interaction count")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c4", action="store_true", help="skip the C4 (10M x 1M, 500M nnz) block")
+    ap.add_argument("--no-ranks", action="store_true", help="skip the predict_ranks block")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -93,26 +93,25 @@ def run(args, rank, world, local):
     clocks = B.ClockSampler(local)
     clocks.start()
 
+    views = None
+
     def make_plan():
         p = fast.ResidentPlan("warp", itf, usf, pos, prob.row, prob.col, prob.data, prob.data, holder, 0.0, 0.0)
         p.set_global_items(n_items_global)
         return p
 
     def step(plan, views, seed):
-        snaps = [v.clone() for v in views]
-        torch.cuda.synchronize(device)
+        # exchange: snapshot sweep, local epoch, delta sweep, ONE all-reduce of the packed user-table
+        # delta (w, g, b, bg), add-back sweep -- all timed on the device (CUDA events)
+        begin_ms = plan.delta_begin(1)
         c = plan.epoch(seed=seed * 977 + rank, num_threads=threads)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        sharding.allreduce_deltas(views, snaps)
-        e1.record()
-        torch.cuda.synchronize(device)
-        c["allreduce_ms"] = e0.elapsed_time(e1)
+        t = sharding.exchange_replicated(plan, 1, device, None, world)
+        c["allreduce_ms"] = t["allreduce_ms"]
+        c["exchange_ms"] = begin_ms + t["make_ms"] + t["allreduce_ms"] + t["apply_ms"]
         return c
 
     # -- value: resident plan; step = local epoch + delta all-reduce ----------------------------
     plan = make_plan()
-    views = user_views(plan, device)
     for w in range(args.warmup):
         step(plan, views, 1000 + w)
     dist.barrier()
@@ -125,14 +124,14 @@ def run(args, rank, world, local):
     wall = time.perf_counter() - t0
     clocks.mark(False)
     clk = clocks.stop()
-    dev_ms = sum(c["kernel_ms"] + c["allreduce_ms"] for c in counters)
+    dev_ms = sum(c["kernel_ms"] + c["exchange_ms"] for c in counters)
     plan.download()
     plan.close()
 
     # -- e2e: host buffers in, host buffers out, every step -------------------------------------
     e2e_ms, h2d = [], 0
     p = make_plan()
-    v = user_views(p, device)
+    v = None
     for s in range(args.warmup + args.steps):
         dist.barrier()
         t0 = time.perf_counter()
@@ -152,9 +151,16 @@ def run(args, rank, world, local):
     sums = torch.tensor([sum(c["positives"] for c in counters), sum(c["negatives_drawn"] for c in counters),
                          sum(c["updates"] for c in counters), sum(c["train_kernel_ms"] for c in counters),
                          sum(B.algorithmic_bytes(c, B.D) for c in counters),
-                         sum(c["kernel_launches"] for c in counters), sum(c["allreduce_ms"] for c in counters)],
+                         sum(c["kernel_launches"] + 3 for c in counters), sum(c["allreduce_ms"] for c in counters),
+                         sum(c["exchange_ms"] for c in counters)],
                         dtype=torch.float64, device=device)
     dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    import bench_c4
+    c4 = None
+    if not getattr(args, "no_c4", False):
+        c4 = bench_c4.run(fast, sharding, dist, rank, world, device, epochs=2,
+                          peak=float(json.load(open(os.path.join(B.ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6567.1))
+                          if os.path.exists(os.path.join(B.ROOT, "MEASURED_PEAKS.json")) else 6567.1)
     if rank == 0:
         positives = sums[0].item()
         value = positives / (stats[0].item() / 1e3)
@@ -170,12 +176,15 @@ def run(args, rank, world, local):
             "warmup": args.warmup, "ms_per_step": stats[0].item() / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "C2 per GPU, item-sharded: 138493 users x %d items, %d nnz, WARP, d=64"
-                                   % (n_items_global, int(positives / args.steps)),
-                       "parallelism": "item-shard x%d + NCCL all-reduce of user-table deltas per epoch" % world,
-                       "l2": "inputs exceed the 126 MB L2",
+            "config": B.base_config(args.nnz),
+            "detail": {"per_gpu_workload": "C2 per GPU, item-sharded: 138493 users x %d items, %d nnz, WARP, d=64"
+                                           % (n_items_global, int(positives / args.steps)),
+                       "parallelism": "item-shard x%d + one NCCL all-reduce of the packed user-table delta per epoch, "
+                                      "subtract / add-back fused into lfm_plan_delta_* sweeps" % world,
                        "wall_ms_per_step": stats[2].item() / args.steps,
-                       "allreduce_ms_per_step": sums[6].item() / world / args.steps},
+                       "allreduce_ms_per_step": sums[6].item() / world / args.steps,
+                       "exchange_ms_per_step": sums[7].item() / world / args.steps},
+            "c4": c4,
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": B.UNIT, "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world, "ms_per_step": stats[1].item() / args.steps,

@@ -242,6 +242,20 @@ int lfm_plan_create(lfm_plan **out, int32_t loss, const lfm_csr *item_features,
  * permutation keyed by `seed` replaces the host shuffle of lightfm.py:689-690. */
 int lfm_plan_epoch(lfm_plan *plan, const int32_t *shuffle_indices, uint32_t seed,
                    int32_t num_threads, lfm_counters *counters);
+/* One pass over interactions [begin, begin + count) of the uploaded list (count < 0: to the end) in
+ * a device-generated random order; hogwild mode only.  Lets a caller cut an epoch into phases. */
+int lfm_plan_epoch_range(lfm_plan *plan, uint32_t seed, int32_t num_threads, int64_t begin,
+                         int64_t count, lfm_counters *counters);
+/* Multi-GPU delta exchange of a replicated table: W <- W0 + sum_g (W_g - W0) for rows
+ * [row_begin, row_begin + row_count) (row_count < 0: to the end) of one side's w, g, b, bg
+ * (side 0 item, 1 user; adagrad state).  begin: snapshot before the local epoch; make: the local
+ * delta as ONE contiguous device buffer (*count floats) for the caller's all-reduce (SUM, in place);
+ * apply: add what the other ranks did.  The subtract / add-back are two sweeps of this library's
+ * kernels; the collective itself is the caller's (NCCL through torch.distributed).  Each call
+ * returns when its sweep is complete; *ms (may be NULL) receives the sweep's device time. */
+int lfm_plan_delta_begin(lfm_plan *plan, int32_t side, int64_t row_begin, int64_t row_count, double *ms);
+int lfm_plan_delta_make(lfm_plan *plan, int32_t side, void **dev_ptr, int64_t *count, double *ms);
+int lfm_plan_delta_apply(lfm_plan *plan, int32_t side, double *ms);
 int lfm_plan_download(lfm_plan *plan, lfm_model *model);
 /* Refresh the resident state arrays and scalar hyper-parameters from `model` (shapes must equal
  * the plan's); interactions, features and the positives lookup stay as uploaded. */

@@ -106,6 +106,11 @@ LIB_ONLY = {
                                   c_f32p, c_f32p, C.c_int64, ModelP, C.c_double, C.c_double,
                                   C.c_int32, C.c_int32]),
     "lfm_plan_epoch": (C.c_int, [C.c_void_p, c_i32p, C.c_uint32, C.c_int32, CountersP]),
+    "lfm_plan_epoch_range": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int32, C.c_int64, C.c_int64, CountersP]),
+    "lfm_plan_delta_begin": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.POINTER(C.c_double)]),
+    "lfm_plan_delta_make": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
+                                      C.POINTER(C.c_double)]),
+    "lfm_plan_delta_apply": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_double)]),
     "lfm_plan_download": (C.c_int, [C.c_void_p, ModelP]),
     "lfm_plan_upload_model": (C.c_int, [C.c_void_p, ModelP]),
     "lfm_evaluate_ranks": (C.c_int, [CsrP, CsrP, CsrP, CsrP, ModelP, C.c_int32, c_i32p, c_f32p, c_f32p,

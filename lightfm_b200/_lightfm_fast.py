@@ -272,6 +272,32 @@ class ResidentPlan(object):
                                    ctypes.byref(cnt)))
         return cnt.as_dict()
 
+    def epoch_range(self, seed, begin, count=-1, num_threads=2):
+        """One pass over interactions [begin, begin + count) of the uploaded list, random order."""
+        cnt = _abi.LfmCounters()
+        _check(_lib.lfm_plan_epoch_range(self._handle, int(seed) & 0xFFFFFFFF, int(num_threads), int(begin),
+                                         int(count), ctypes.byref(cnt)))
+        return cnt.as_dict()
+
+    def delta_begin(self, side, row_begin=0, row_count=-1):
+        """Snapshot rows of one side's w, g, b, bg before a local epoch (side 0 item, 1 user)."""
+        ms = ctypes.c_double()
+        _check(_lib.lfm_plan_delta_begin(self._handle, int(side), int(row_begin), int(row_count), ctypes.byref(ms)))
+        return ms.value
+
+    def delta_make(self, side):
+        """(device pointer, float count, sweep ms) of the local delta since ``delta_begin``: all-reduce it."""
+        ptr, cnt, ms = ctypes.c_void_p(), ctypes.c_int64(), ctypes.c_double()
+        _check(_lib.lfm_plan_delta_make(self._handle, int(side), ctypes.byref(ptr), ctypes.byref(cnt),
+                                        ctypes.byref(ms)))
+        return ptr.value, cnt.value, ms.value
+
+    def delta_apply(self, side):
+        """Add the other ranks' share of the all-reduced delta to the resident table (returns sweep ms)."""
+        ms = ctypes.c_double()
+        _check(_lib.lfm_plan_delta_apply(self._handle, int(side), ctypes.byref(ms)))
+        return ms.value
+
     def download(self):
         _check(_lib.lfm_plan_download(self._handle, self._lightfm.ptr))
 

@@ -75,6 +75,7 @@ struct FitArgs {
     const double* loss_table;      // [max_sampled + 1] log terms precomputed on the host
     const float* loss_table_f;     // the same terms rounded to float (hogwild kernels)
     int64_t t_offset;              // index of this launch's first tuple in the epoch (Philox counter base)
+    int64_t row_offset;            // first interaction (upload order) this epoch visits; it visits n of them
     DevCounters* counters;
     DevScales* scales;
     // Optional exact membership bitmap of the positives CSR: bit (u, i) at
@@ -99,6 +100,16 @@ cudaError_t lfm_launch_replay(int loss, const FitArgs& a, cudaStream_t st);
 cudaError_t lfm_launch_hogwild(int loss, const FitArgs& a, Tuple* tuples, cudaStream_t st,
                                int* launches, cudaEvent_t ev_train_begin, cudaEvent_t ev_train_end);
 cudaError_t lfm_launch_regularize(const DevModel& m, DevScales* scales, cudaStream_t st);
+// Delta exchange of a replicated table (multi-GPU): up to four (pointer, count)
+// segments -- rows [begin, begin+count) of w, g, b, bg -- addressed as one flat range.
+struct DeltaSegs {
+    float* p[4];
+    int64_t n[4];
+};
+// mode 0: S = cur                      (snapshot before the local epoch)
+// mode 1: D = cur - S ; S = D          (local delta, kept in S; D goes to the all-reduce)
+// mode 2: cur = cur + D - S            (add what the OTHER ranks did: reduced sum minus own delta)
+cudaError_t lfm_launch_delta(int mode, const DeltaSegs& segs, float* S, float* D, cudaStream_t st);
 cudaError_t lfm_launch_predict(const DevCsr& itf, const DevCsr& usf, const DevModel& m,
                                const int32_t* user_ids, const int32_t* item_ids, float* out,
                                int64_t n, cudaStream_t st);

@@ -50,11 +50,11 @@ __device__ __forceinline__ int64_t feistel_perm(int64_t i, int64_t n, int hb, ui
 __global__ void pack_kernel(const int32_t* __restrict__ user_ids, const int32_t* __restrict__ item_ids,
                             const float* __restrict__ y, const float* __restrict__ w,
                             const int32_t* __restrict__ shuffle, int64_t n, int hb, uint32_t key,
-                            int skip_nonpositive, int unit_weights, Tuple* __restrict__ out) {
+                            int skip_nonpositive, int unit_weights, int64_t row_offset, Tuple* __restrict__ out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
-        int64_t row = shuffle ? (int64_t)shuffle[i] : feistel_perm(i, n, hb, key);
+        int64_t row = shuffle ? (int64_t)shuffle[i] : row_offset + feistel_perm(i, n, hb, key);
         Tuple t;
         t.user = user_ids[row];
         t.item = item_ids ? item_ids[row] : (int32_t)i;  // k-OS: the tuple's index in the epoch
@@ -687,6 +687,21 @@ __global__ void __launch_bounds__(HOT ? 512 : 256) hogwild_kernel(FitArgs a, con
     }
 }
 
+__global__ void delta_kernel(int mode, DeltaSegs segs, float* __restrict__ S, float* __restrict__ D) {
+    const int64_t total = segs.n[0] + segs.n[1] + segs.n[2] + segs.n[3];
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        int64_t j = i;
+        int s = 0;
+        while (j >= segs.n[s]) { j -= segs.n[s]; s++; }
+        float* cur = segs.p[s] + j;
+        if (mode == 0) S[i] = *cur;
+        else if (mode == 1) { const float dlt = *cur - S[i]; D[i] = dlt; S[i] = dlt; }
+        else *cur = *cur + (D[i] - S[i]);
+    }
+}
+
 // Hogwild-mode regularize: scales live in the log domain.
 __global__ void regularize_log_kernel(DevModel m, DevScales* scales) {
     float is = (float)exp(scales->item_scale), us = (float)exp(scales->user_scale);
@@ -860,6 +875,15 @@ cudaError_t lfm_launch_build_bitmap(const DevCsr& pos, uint32_t* bitmap, int32_t
     return cudaGetLastError();
 }
 
+cudaError_t lfm_launch_delta(int mode, const DeltaSegs& segs, float* S, float* D, cudaStream_t st) {
+    const int64_t total = segs.n[0] + segs.n[1] + segs.n[2] + segs.n[3];
+    if (total == 0) return cudaSuccess;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    delta_kernel<<<(int)blocks, 256, 0, st>>>(mode, segs, S, D);
+    return cudaGetLastError();
+}
+
 // Host-visible helper: is (loss, model, features) eligible for the hogwild path at all?
 int lfm_hogwild_supported(int loss, int d, int nkos) {
     if (d < 1 || d > 256) return 0;
@@ -880,7 +904,7 @@ cudaError_t lfm_launch_pack(const FitArgs& a, int loss, Tuple* tuples, uint32_t 
     pack_kernel<<<(int)blocks, 256, 0, st>>>(a.user_ids, loss == LOSS_KOS ? nullptr : a.item_ids,
                                              loss == LOSS_KOS ? nullptr : a.y,
                                              loss == LOSS_KOS ? nullptr : a.sample_weight, a.shuffle,
-                                             a.n, hb, perm_key, skip, a.unit_weights, tuples);
+                                             a.n, hb, perm_key, skip, a.unit_weights, a.row_offset, tuples);
     return cudaGetLastError();
 }
 

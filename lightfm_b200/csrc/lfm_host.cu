@@ -910,6 +910,11 @@ struct lfm_plan {
     int loss = 0;
     int nkos = 0;
     bool has_shuffle_buf = false;
+    // delta exchange of a replicated table (lfm_plan_delta_*): per side (0 item, 1 user)
+    DeltaSegs segs[2] = {};
+    float* dS[2] = {nullptr, nullptr};
+    float* dD[2] = {nullptr, nullptr};
+    int dstate[2] = {0, 0};  // 0 idle, 1 snapshot taken, 2 delta made
 };
 
 extern "C" int lfm_plan_create(lfm_plan** out, int32_t loss, const lfm_csr* item_features,
@@ -999,15 +1004,28 @@ extern "C" int lfm_plan_create(lfm_plan** out, int32_t loss, const lfm_csr* item
 
 // One epoch on resident data.  shuffle_indices == NULL: the visiting order is a fresh
 // pseudo-random permutation generated on the device from `seed` (hogwild mode only).
-extern "C" int lfm_plan_epoch(lfm_plan* p, const int32_t* shuffle_indices, uint32_t seed,
-                              int32_t num_threads, lfm_counters* counters) {
+static int plan_epoch_impl(lfm_plan* p, const int32_t* shuffle_indices, uint32_t seed, int32_t num_threads,
+                           int64_t begin, int64_t count, lfm_counters* counters) {
     std::lock_guard<std::mutex> lock(g_mu);
     if (!p) return fail(LFM_ERR_ARG, "null plan");
     if (counters) memset(counters, 0, sizeof(*counters));
     g_cur = &p->arena;
     struct Restore { ~Restore() { g_cur = &g_arena; } } restore;
     Staged& st = p->st;
+    const int64_t n_total = st.a.n_all;
+    if (count < 0) count = n_total - begin;
+    if (begin < 0 || begin + count > n_total) return fail(LFM_ERR_ARG, "interaction range out of bounds");
+    if ((begin != 0 || count != n_total) && shuffle_indices)
+        return fail(LFM_ERR_ARG, "a sub-range epoch uses the device-generated order (shuffle_indices must be NULL)");
+    struct RangeGuard {  // the staged arguments describe the whole problem again when we leave
+        FitArgs& a; int64_t n;
+        ~RangeGuard() { a.n = n; a.row_offset = 0; }
+    } range_guard{st.a, n_total};
+    st.a.n = count;
+    st.a.row_offset = begin;
     const int mode = resolve_mode(num_threads, p->loss, st.a.model.d, p->nkos);
+    if (mode != LFM_MODE_HOGWILD && (begin != 0 || count != n_total))
+        return fail(LFM_ERR_ARG, "a sub-range epoch runs in hogwild mode only");
     if (p->loss != LOSS_LOGISTIC && st.a.pos.indptr == nullptr &&
         (mode != LFM_MODE_HOGWILD || !lfm_fast_path_eligible(p->loss, st.a, st.a.n)))
         return fail(LFM_ERR_STATE, "this plan has no positives CSR (bitmap only): it can only run the "
@@ -1016,7 +1034,7 @@ extern "C" int lfm_plan_epoch(lfm_plan* p, const int32_t* shuffle_indices, uint3
     CU(cudaEventRecord(g_ev[0], g_stream));
     if (shuffle_indices) {
         int32_t* d = nullptr;
-        int rc = upload("fit.shuffle", shuffle_indices, (size_t)st.a.n, &d, x);
+        int rc = upload("fit.shuffle", shuffle_indices, (size_t)st.a.n_all, &d, x);
         if (rc != LFM_OK) return rc;
         st.a.shuffle = d;
     } else {
@@ -1037,6 +1055,92 @@ extern "C" int lfm_plan_epoch(lfm_plan* p, const int32_t* shuffle_indices, uint3
     cudaEventElapsedTime(&ms_k, g_ev[1], g_ev[2]);
     cudaEventElapsedTime(&ms_d2h, g_ev[2], g_ev[3]);
     fill_counters(counters, hc, x, launches, mode, ms_h2d, ms_k, ms_d2h);
+    return LFM_OK;
+}
+
+extern "C" int lfm_plan_epoch(lfm_plan* p, const int32_t* shuffle_indices, uint32_t seed,
+                              int32_t num_threads, lfm_counters* counters) {
+    return plan_epoch_impl(p, shuffle_indices, seed, num_threads, 0, -1, counters);
+}
+
+// One pass over interactions [begin, begin + count) of the uploaded list, in a device-generated
+// random order (hogwild mode).  Lets a caller cut an epoch into phases (e.g. by user block) and
+// interleave its own collectives between them.
+extern "C" int lfm_plan_epoch_range(lfm_plan* p, uint32_t seed, int32_t num_threads, int64_t begin,
+                                    int64_t count, lfm_counters* counters) {
+    return plan_epoch_impl(p, nullptr, seed, num_threads, begin, count, counters);
+}
+
+// ---- delta exchange of a replicated table (multi-GPU) -------------------------------
+// W <- W0 + sum_g (W_g - W0) for rows [row_begin, row_begin + row_count) of one side's w, g, b, bg,
+// with the subtract / add-back fused into two sweeps of our own kernels and ONE contiguous buffer
+// for the caller's collective (NCCL all-reduce over torch.distributed):
+//     lfm_plan_delta_begin   S = cur                       (before the local epoch)
+//     lfm_plan_delta_make    D = cur - S, S = D            -> *dev_ptr = D, *count floats: all-reduce it (SUM) in place
+//     lfm_plan_delta_apply   cur += D - S                  (what the other ranks did)
+// side: 0 item table, 1 user table.
+static int timed_delta(int mode, const DeltaSegs& sg, float* S, float* D, double* ms) {
+    CU(cudaEventRecord(g_ev[0], g_stream));
+    CU(lfm_launch_delta(mode, sg, S, D, g_stream));
+    CU(cudaEventRecord(g_ev[1], g_stream));
+    CU(cudaStreamSynchronize(g_stream));  // the caller's collective runs on another stream
+    if (ms) {
+        float f = 0;
+        cudaEventElapsedTime(&f, g_ev[0], g_ev[1]);
+        *ms = f;
+    }
+    return LFM_OK;
+}
+
+extern "C" int lfm_plan_delta_begin(lfm_plan* p, int32_t side, int64_t row_begin, int64_t row_count, double* ms) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (!p || side < 0 || side > 1) return fail(LFM_ERR_ARG, "bad plan / side");
+    const DevModel& m = p->st.a.model;
+    const DevTable& t = side == 0 ? m.item : m.user;
+    if (row_count < 0) row_count = t.n - row_begin;
+    if (row_begin < 0 || row_begin + row_count > t.n) return fail(LFM_ERR_ARG, "row range out of bounds");
+    if (m.adadelta) return fail(LFM_ERR_ARG, "the delta exchange covers the adagrad state (w, g, b, bg)");
+    g_cur = &p->arena;
+    struct Restore { ~Restore() { g_cur = &g_arena; } } restore;
+    DeltaSegs& sg = p->segs[side];
+    sg.p[0] = t.w + row_begin * m.d;  sg.n[0] = row_count * m.d;
+    sg.p[1] = t.g + row_begin * m.d;  sg.n[1] = row_count * m.d;
+    sg.p[2] = t.b + row_begin;        sg.n[2] = row_count;
+    sg.p[3] = t.bg + row_begin;       sg.n[3] = row_count;
+    const size_t total = (size_t)(2 * row_count * m.d + 2 * row_count);
+    void *s = nullptr, *d = nullptr;
+    int rc = arena_get(side == 0 ? "delta.S.item" : "delta.S.user", sizeof(float) * total, &s);
+    if (rc != LFM_OK) return rc;
+    rc = arena_get(side == 0 ? "delta.D.item" : "delta.D.user", sizeof(float) * total, &d);
+    if (rc != LFM_OK) return rc;
+    p->dS[side] = (float*)s;
+    p->dD[side] = (float*)d;
+    rc = timed_delta(0, sg, p->dS[side], p->dD[side], ms);
+    if (rc != LFM_OK) return rc;
+    p->dstate[side] = 1;
+    return LFM_OK;
+}
+
+extern "C" int lfm_plan_delta_make(lfm_plan* p, int32_t side, void** dev_ptr, int64_t* count, double* ms) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (!p || side < 0 || side > 1 || !dev_ptr || !count) return fail(LFM_ERR_ARG, "bad argument");
+    if (p->dstate[side] != 1) return fail(LFM_ERR_STATE, "lfm_plan_delta_begin was not called");
+    const DeltaSegs& sg = p->segs[side];
+    int rc = timed_delta(1, sg, p->dS[side], p->dD[side], ms);
+    if (rc != LFM_OK) return rc;
+    *dev_ptr = p->dD[side];
+    *count = sg.n[0] + sg.n[1] + sg.n[2] + sg.n[3];
+    p->dstate[side] = 2;
+    return LFM_OK;
+}
+
+extern "C" int lfm_plan_delta_apply(lfm_plan* p, int32_t side, double* ms) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (!p || side < 0 || side > 1) return fail(LFM_ERR_ARG, "bad argument");
+    if (p->dstate[side] != 2) return fail(LFM_ERR_STATE, "lfm_plan_delta_make was not called");
+    int rc = timed_delta(2, p->segs[side], p->dS[side], p->dD[side], ms);
+    if (rc != LFM_OK) return rc;
+    p->dstate[side] = 0;
     return LFM_OK;
 }
 

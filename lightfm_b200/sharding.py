@@ -109,6 +109,27 @@ def allreduce_deltas(tensors, snapshots, group=None):
         t.add_(s)
 
 
+def exchange_replicated(plan, side, device, group=None, world=None):
+    """One delta exchange of the replicated table of a resident plan:
+    ``W <- W0 + sum_g (W_g - W0)`` for w, g, b, bg of `side` (0 item, 1 user).  Call
+    ``plan.delta_begin(side)`` before the local epoch and this afterwards.  The subtract and
+    add-back are two sweeps of libfm_cuda's own kernels over ONE packed buffer, which is
+    all-reduced in place with a single NCCL call.  Returns the device milliseconds
+    ``{"make_ms", "allreduce_ms", "apply_ms"}`` (CUDA events)."""
+    import torch
+    import torch.distributed as dist
+    ptr, count, make_ms = plan.delta_make(side)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    if dist.is_initialized() and (world is None or world > 1):
+        t = torch.as_tensor(CudaArrayView(ptr, count), device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    e1.record()
+    torch.cuda.synchronize(device)
+    apply_ms = plan.delta_apply(side)
+    return {"make_ms": make_ms, "allreduce_ms": e0.elapsed_time(e1), "apply_ms": apply_ms}
+
+
 class CudaArrayView(object):
     """Expose a raw device pointer as ``__cuda_array_interface__`` so torch can wrap it
     (``torch.as_tensor(view, device=...)``) without copying."""
@@ -134,8 +155,6 @@ class ShardedTrainer(object):
 
     Identity features only (see module docstring).
     """
-
-    REPLICATED_TABLES = {"item": (6, 7, 9, 10), "user": (0, 1, 3, 4)}  # lfm_plan_table ids: w, g, b, bg
 
     def __init__(self, model, interactions, axis="item", sample_weight=None, group=None, device=None):
         import torch
@@ -178,25 +197,20 @@ class ShardedTrainer(object):
             model.item_alpha, model.user_alpha, model.k, model.n)
         if axis == "item":
             self.plan.set_global_items(n_items)
-        import torch as _t
-        self.views = [_t.as_tensor(CudaArrayView(*self.plan.table(w)), device=self.device)
-                      for w in self.REPLICATED_TABLES[axis]]
+        self.replicated_side = 1 if axis == "item" else 0   # lfm_plan_delta_* side: 0 item, 1 user
         self.local_interactions = local.nnz
         self.last_counters = None
 
     def epoch(self, seed, num_threads=8):
         """One local epoch + the delta all-reduce of the replicated table."""
-        import torch
-        snaps = [v.clone() for v in self.views]
-        torch.cuda.synchronize(self.device)
+        side = self.replicated_side
+        begin_ms = self.plan.delta_begin(side) if self.world > 1 else 0.0
         c = self.plan.epoch(seed=(int(seed) * 977 + self.rank) & 0xFFFFFFFF, num_threads=max(2, num_threads))
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        c["allreduce_ms"] = c["exchange_ms"] = 0.0
         if self.world > 1:
-            allreduce_deltas(self.views, snaps, self.group)
-        e1.record()
-        torch.cuda.synchronize(self.device)
-        c["allreduce_ms"] = e0.elapsed_time(e1)
+            t = exchange_replicated(self.plan, side, self.device, self.group, self.world)
+            c["allreduce_ms"] = t["allreduce_ms"]
+            c["exchange_ms"] = begin_ms + t["make_ms"] + t["allreduce_ms"] + t["apply_ms"]
         self.last_counters = c
         return c
 

@@ -462,6 +462,16 @@ def run_ours(args):
         except Exception as exc:  # pragma: no cover
             c4 = {"error": "%s: %s" % (type(exc).__name__, exc)}
 
+    ranks = None
+    if not args.no_ranks:
+        try:
+            fast.release_cache()
+            ranks = ranks_block(fast, with_cpu=not args.no_cpu_baseline)
+            launches += 3 + 6 + 4
+            fast.release_cache()
+        except Exception as exc:  # pragma: no cover
+            ranks = {"error": "%s: %s" % (type(exc).__name__, exc)}
+
     mean = lambda k: sum(c[k] for c in counters) / len(counters)
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
@@ -493,8 +503,92 @@ def run_ours(args):
         "parity": parity,
         "cpu_baseline": cpu,
         "c4": c4,
+        "ranks": ranks,
     }
     print(json.dumps(out))
+
+
+def ranks_block(fast, with_cpu=True):
+    """predict_ranks / fused evaluation / top-k at BASELINE config 5's shape (1 M users x 100 k items,
+    d=32) on a 20 000-user slice: user-item scores per second and FP32 (non-FMA: the score is a
+    multiply and a separately rounded add per component, for bit parity) throughput."""
+    import torch
+    n_users, n_items, d, slice_users = 1_000_000, 100_000, 32, 20_000
+    rng = np.random.default_rng(0)
+    st = []
+    for n in (n_items, n_users):
+        st += [(rng.standard_normal((n, d), dtype=np.float32) * 0.1), np.ones((n, d), np.float32),
+               np.zeros((n, d), np.float32), (rng.standard_normal(n, dtype=np.float32) * 0.1),
+               np.ones(n, np.float32), np.zeros(n, np.float32)]
+    holder = fast.FastLightFM(*st, d, 0, 0.05, 0.95, 1e-6, 10)
+    mk = lambda per: (np.repeat(np.arange(slice_users), per), None)
+    rows = np.repeat(np.arange(slice_users), 10)
+    test = sp.csr_matrix((np.ones(rows.size, np.float32), (rows, rng.integers(0, n_items, rows.size))), shape=(n_users, n_items))
+    rows = np.repeat(np.arange(slice_users), 100)
+    train = sp.csr_matrix((np.ones(rows.size, np.float32), (rows, rng.integers(0, n_items, rows.size))), shape=(n_users, n_items))
+    train = train - train.multiply(test)            # no intersections
+    for m in (test, train):
+        m.sum_duplicates()
+        m.eliminate_zeros()
+        m.sort_indices()
+    test, train = test.astype(np.float32), train.astype(np.float32)
+    itf = sp.identity(n_items, dtype=np.float32, format="csr")
+    usf = sp.identity(n_users, dtype=np.float32, format="csr")
+    ci, cu, ct, ctr = fast.CSRMatrix(itf), fast.CSRMatrix(usf), fast.CSRMatrix(test), fast.CSRMatrix(train)
+    scores = float(slice_users) * n_items
+    flop = scores * (2 * d + 1)
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    peak_tf = sms * 128 * 1.965e9 / 1e12     # FP32 instructions/s at the boost clock, one flop each (no FMA)
+    out = {"workload": "C5 slice: %d of 1M users x 100k items, d=32, %d test + %d train interactions"
+                       % (slice_users, test.nnz, train.nnz),
+           "fp32_nonfma_peak_TFLOPs": peak_tf}
+    for rep in range(2):
+        ranks = np.zeros_like(test.data)
+        t0 = time.perf_counter()
+        fast.predict_ranks(ci, cu, ct, ctr, ranks, holder, 8)
+        wall = time.perf_counter() - t0
+    kms = fast.last_scoring_ms()
+    out["predict_ranks"] = {"kernel_ms": kms, "call_wall_ms": 1e3 * wall, "G_scores_per_s_kernel": scores / kms / 1e6,
+                            "G_scores_per_s_call": scores / wall / 1e9, "TFLOPs_kernel": flop / kms / 1e9,
+                            "frac_of_fp32_nonfma_peak": flop / kms / 1e9 / peak_tf,
+                            "d2h_bytes": int(ranks.nbytes), "note": "call = model upload (141 MB) + kernels + ranks download"}
+    t0 = time.perf_counter()
+    hits, best, auc = fast.evaluate_ranks(ci, cu, ct, ctr, holder, 10, num_threads=8)
+    wall = time.perf_counter() - t0
+    out["evaluate_ranks_fused"] = {"kernel_ms": fast.last_scoring_ms(), "call_wall_ms": 1e3 * wall,
+                                   "d2h_bytes": int(hits.nbytes + best.nbytes + auc.nbytes),
+                                   "precision_at_10": float((hits[:slice_users] / 10.0).mean()),
+                                   "auc": float(auc[:slice_users].mean())}
+    users = np.arange(slice_users, dtype=np.int32)
+    t0 = time.perf_counter()
+    items, sc = fast.recommend(ci, cu, ctr, users, n_items, 10, holder)
+    wall = time.perf_counter() - t0
+    out["recommend_top10"] = {"kernel_ms": fast.last_scoring_ms(), "call_wall_ms": 1e3 * wall,
+                              "users_per_s_call": slice_users / wall}
+    if with_cpu:
+        try:
+            ref_fast, kind = load_reference_native()
+            cpu_users = 200
+            tsub = test[:cpu_users].copy()
+            tsub.resize((n_users, n_items))
+            tsub = sp.csr_matrix(tsub, dtype=np.float32)
+            tsub.sort_indices()
+            rk = np.zeros_like(tsub.data)
+            threads = min(os.cpu_count() or 1, 32)
+            t0 = time.perf_counter()
+            ref_fast.predict_ranks(ref_fast.CSRMatrix(itf), ref_fast.CSRMatrix(usf), ref_fast.CSRMatrix(tsub),
+                                   ref_fast.CSRMatrix(train), rk, holder_for(ref_fast, st, d), threads)
+            dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": cpu_users * n_items / dt, "unit": "user-item scores/s", "cores": threads,
+                                   "kind": "reference", "sample": "reference predict_ranks on the first %d users of the slice" % cpu_users,
+                                   "ranks_equal_gpu": bool(np.array_equal(rk, ranks[:len(rk)]))}
+        except Exception as exc:  # pragma: no cover
+            out["cpu_baseline"] = {"value": None, "sample": "unavailable: %s" % exc}
+    return out
+
+
+def holder_for(api, st, d):
+    return api.FastLightFM(*st, d, 0, 0.05, 0.95, 1e-6, 10)
 
 
 def parity_and_baseline(fast, prob, threads):

@@ -221,6 +221,10 @@ int lfm_recommend(const lfm_csr *item_features, const lfm_csr *user_features, co
                   const int32_t *user_ids, int64_t n_users, int32_t n_items, int32_t k,
                   const lfm_model *model, int32_t *out_items, float *out_scores);
 
+/* Device milliseconds spanned by the kernels of the most recent predict_ranks / evaluate_ranks /
+ * recommend call (CUDA events on the library's stream). */
+int lfm_last_scoring_ms(double *ms);
+
 /* T:1380-1385 (test hook; runs the device membership search). Returns 0/1, <0 on error. */
 int lfm_test_in_positives(int32_t row, int32_t col, const lfm_csr *mat);
 

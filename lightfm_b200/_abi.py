@@ -117,6 +117,7 @@ LIB_ONLY = {
                                      C.c_int32]),
     "lfm_recommend": (C.c_int, [CsrP, CsrP, CsrP, c_i32p, C.c_int64, C.c_int32, C.c_int32, ModelP,
                                 c_i32p, c_f32p]),
+    "lfm_last_scoring_ms": (C.c_int, [C.POINTER(C.c_double)]),
     "lfm_pin_host": (C.c_int, [C.c_void_p, C.c_int64]),
     "lfm_unpin_host": (C.c_int, [C.c_void_p]),
     "lfm_set_tuning": (C.c_int, [C.c_int]),

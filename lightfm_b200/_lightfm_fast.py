@@ -201,6 +201,13 @@ def evaluate_ranks(item_features, user_features, test_interactions, train_intera
     return hits, best, auc
 
 
+def last_scoring_ms():
+    """Device milliseconds of the kernels of the last predict_ranks / evaluate_ranks / recommend call."""
+    ms = ctypes.c_double()
+    _check(_lib.lfm_last_scoring_ms(ctypes.byref(ms)))
+    return ms.value
+
+
 def recommend(item_features, user_features, exclude, user_ids, n_items, k, lightfm):
     """Top-k items per user (``lfm_recommend``): (items int32[n, k], scores float32[n, k])."""
     _abi._require(user_ids, np.int32, 1, "user_ids")

@@ -53,6 +53,7 @@ Arena* g_cur = &g_arena;  // arena the staging helpers allocate from (global, or
 cudaStream_t g_stream = nullptr;
 cudaEvent_t g_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 bool g_init = false;
+bool g_scoring_timed = false;  // g_ev[4..5] bracket the kernels of the last scoring call
 
 int ensure_init() {
     if (g_init) return LFM_OK;
@@ -705,7 +706,10 @@ extern "C" int lfm_predict_ranks(const lfm_csr* item_features, const lfm_csr* us
     rc = arena_get("ranks.scratch", sizeof(float) * lfm_ranks_scratch_floats(test.cols, dm.d, test.rows), &p);
     if (rc != LFM_OK) return rc;
     int launches = 0;
+    CU(cudaEventRecord(g_ev[4], g_stream));
     CU(lfm_launch_predict_ranks(itf, usf, test, train, dm, d_ranks, (float*)p, g_stream, &launches));
+    CU(cudaEventRecord(g_ev[5], g_stream));
+    g_scoring_timed = true;
     rc = download(ranks, (const float*)d_ranks, (size_t)test.nnz, x);
     if (rc != LFM_OK) return rc;
     CU(cudaStreamSynchronize(g_stream));
@@ -801,6 +805,7 @@ extern "C" int lfm_evaluate_ranks(const lfm_csr* item_features, const lfm_csr* u
     if (rc != LFM_OK) return rc;
     CU(cudaMemsetAsync(d_ranks, 0, sizeof(float) * nnz, g_stream));
     int launches = 0;
+    CU(cudaEventRecord(g_ev[4], g_stream));
     CU(lfm_launch_predict_ranks(itf, usf, test, train, dm, (float*)d_ranks, (float*)p, g_stream, &launches));
     if (hits || best_rank) CU(lfm_launch_rank_metrics(test, (const float*)d_ranks, k, (int32_t*)d_hits, (float*)d_best, g_stream));
     if (auc) {
@@ -808,6 +813,8 @@ extern "C" int lfm_evaluate_ranks(const lfm_csr* item_features, const lfm_csr* u
         CU(cudaMemsetAsync(d_auc, 0, sizeof(float) * rows, g_stream));
         CU(lfm_launch_auc(test, (const int32_t*)d_ntp, (float*)d_ranks, (float*)d_auc, (float*)d_tmp, g_stream));
     }
+    CU(cudaEventRecord(g_ev[5], g_stream));
+    g_scoring_timed = true;
     if (hits) { rc = download(hits, (const int32_t*)d_hits, rows, x); if (rc != LFM_OK) return rc; }
     if (best_rank) { rc = download(best_rank, (const float*)d_best, rows, x); if (rc != LFM_OK) return rc; }
     if (auc) { rc = download(auc, (const float*)d_auc, rows, x); if (rc != LFM_OK) return rc; }
@@ -862,6 +869,7 @@ extern "C" int lfm_recommend(const lfm_csr* item_features, const lfm_csr* user_f
     int32_t* d_users = nullptr;
     rc = upload("rec.users", user_ids, (size_t)n_users, &d_users, x);
     if (rc != LFM_OK) return rc;
+    CU(cudaEventRecord(g_ev[4], g_stream));
     for (int64_t b0 = 0; b0 < n_users; b0 += batch) {
         const int nb = (int)((n_users - b0 < batch) ? (n_users - b0) : batch);
         int launches = 0;
@@ -873,6 +881,21 @@ extern "C" int lfm_recommend(const lfm_csr* item_features, const lfm_csr* user_f
         if (rc != LFM_OK) return rc;
         CU(cudaStreamSynchronize(g_stream));
     }
+    CU(cudaEventRecord(g_ev[5], g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    g_scoring_timed = true;
+    return LFM_OK;
+}
+
+// Device time (ms) between the first and last kernel of the most recent predict_ranks /
+// evaluate_ranks / recommend call (for recommend: including the per-batch result copies).
+extern "C" int lfm_last_scoring_ms(double* ms) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (!ms) return fail(LFM_ERR_ARG, "null argument");
+    if (!g_init || !g_scoring_timed) return fail(LFM_ERR_STATE, "no scoring call has run yet");
+    float f = 0;
+    CU(cudaEventElapsedTime(&f, g_ev[4], g_ev[5]));
+    *ms = f;
     return LFM_OK;
 }
 

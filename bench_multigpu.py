@@ -155,12 +155,21 @@ def run(args, rank, world, local):
                          sum(c["exchange_ms"] for c in counters)],
                         dtype=torch.float64, device=device)
     dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    import bench_c4
+    # C4 runs AFTER every collective the headline numbers depend on, under try/except on every rank:
+    # a failure there (or a rank that cannot follow: the process-group timeout turns a hang into an
+    # exception) costs the c4 block, not the line.
     c4 = None
     if not getattr(args, "no_c4", False):
-        c4 = bench_c4.run(fast, sharding, dist, rank, world, device, epochs=2,
-                          peak=float(json.load(open(os.path.join(B.ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6567.1))
-                          if os.path.exists(os.path.join(B.ROOT, "MEASURED_PEAKS.json")) else 6567.1)
+        try:
+            import bench_c4
+            pk = 6567.1
+            try:
+                pk = float(json.load(open(os.path.join(B.ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+            except Exception:
+                pass
+            c4 = bench_c4.run(fast, sharding, dist, rank, world, device, epochs=2, peak=pk)
+        except Exception as exc:  # pragma: no cover
+            c4 = {"error": "%s: %s" % (type(exc).__name__, exc)}
     if rank == 0:
         positives = sums[0].item()
         value = positives / (stats[0].item() / 1e3)
@@ -195,5 +204,8 @@ def run(args, rank, world, local):
                          "note": "per-GPU average"},
             "cpu_baseline": None,
         }))
-    dist.barrier()
-    dist.destroy_process_group()
+    try:
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:  # pragma: no cover
+        pass

@@ -141,6 +141,9 @@ int lfm_set_fast_path(int enabled);
 int lfm_set_inflight_divisor(int divisor);
 /* 0: disable the per-CTA shared-memory aggregation of hot feature rows (feature path; tests / A-B timing). */
 int lfm_set_hot_rows(int enabled);
+/* 0: always use the general replay kernel (the prefetching WARP replay kernel is the default where
+ * it applies: identity features, adagrad, alpha == 0); both are bit-equal to the oracle. */
+int lfm_set_replay_fast(int enabled);
 /* 1: run the slot kernels as ONE warp with ONE interaction in flight and the reference's rand_r
  * negatives, so that only their arithmetic differs from the oracle (tests/test_gpu_probe.py). */
 int lfm_set_probe(int enabled);

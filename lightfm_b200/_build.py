@@ -23,7 +23,7 @@ SOURCES = [
     ("lfm_hogwild.cu", []),
     ("lfm_host.cu", []),
 ]
-HEADERS = ["lfm_common.cuh", "lfm_hogwild_fast.cuh", os.path.join("..", "..", "include", "lfm_cuda.h")]
+HEADERS = ["lfm_common.cuh", "lfm_hogwild_fast.cuh", "lfm_replay_fast.cuh", os.path.join("..", "..", "include", "lfm_cuda.h")]
 
 
 def _nvcc():
@@ -58,11 +58,13 @@ def build(force=False, verbose=False):
             if r.returncode != 0:
                 raise RuntimeError("nvcc failed on %s" % src)
     if force or _stale(OUT, objs):
-        cmd = [nvcc] + ARCH + ["-shared", "-o", OUT] + objs
+        tmp = OUT + ".tmp.%d" % os.getpid()   # link aside, then rename: the library is never half-written
+        cmd = [nvcc] + ARCH + ["-shared", "-o", tmp] + objs
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout)
             raise RuntimeError("link failed")
+        os.replace(tmp, OUT)
     return OUT
 
 

@@ -86,6 +86,11 @@ def set_probe(enabled):
     return _lib.lfm_set_probe(int(bool(enabled)))
 
 
+def set_replay_fast(enabled):
+    """Replay mode: use the prefetching WARP kernel where it applies (default on; both bit-equal)."""
+    return _lib.lfm_set_replay_fast(int(bool(enabled)))
+
+
 def set_hot_rows(enabled):
     """Feature path: per-CTA shared-memory aggregation of hot feature rows (default on)."""
     return _lib.lfm_set_hot_rows(int(bool(enabled)))
@@ -104,7 +109,8 @@ def set_tuning(variant):
 
 _TUNING_NAMES = {0: "fast_rank_kernel<WARP,LPR=d/4>", 4: "fast_slot_kernel<WARP,d,1,3>", 5: "fast_slot_kernel<WARP,d,1,4>",
                  6: "fast_slot_kernel<WARP,d,2,2>", 7: "fast_slot_kernel<WARP,d,2,3>",
-                 8: "fast_slot_kernel<WARP,d,2,4>"}
+                 8: "fast_slot_kernel<WARP,d,2,4>", 9: "fast_slot_kernel<WARP,d,2,3,SPEC>",
+                 10: "fast_slot_kernel<WARP,d,2,2,SPEC>"}
 
 
 def warp_kernel_name(d=64):

@@ -332,7 +332,12 @@ __device__ __forceinline__ int slot_probe_index(int lo, int hi, int sub) {
 // Philox.  What is left to differ from the oracle is exactly this kernel's arithmetic (fp32
 // temporaries, FMA, lr * rsqrt.approx(G), float log table) -- tests/test_gpu_probe.py states by
 // how much.
-template <int LOSS, int D, int VPL, int MINB, bool BITMAP = false, int KSR = 1, bool PROBE = false>
+//
+// SPEC (WARP / k-OS, lfm_set_tuning(9)): two candidates per slot per round -- both rows are
+// requested together and judged in draw order, so the outcome is exactly that of drawing them one
+// at a time (the second one is simply not consumed when the first is taken), while the number of
+// dependent L2 round trips per interaction is halved.
+template <int LOSS, int D, int VPL, int MINB, bool BITMAP = false, int KSR = 1, bool PROBE = false, bool SPEC = false>
 __global__ void __launch_bounds__(256, MINB) fast_slot_kernel(FitArgs a, const Tuple* __restrict__ tuples) {
     constexpr bool PAIRWISE = LOSS != LOSS_LOGISTIC;  // has a negative item and a positives CSR
     constexpr bool KOS = LOSS == LOSS_KOS;            // positive item chosen in-kernel (T:975-1011)
@@ -513,7 +518,69 @@ __global__ void __launch_bounds__(256, MINB) fast_slot_kernel(FitArgs a, const T
 #pragma unroll
         for (int v = 0; v < VPL; v++) q[v] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-        if constexpr (LOSS == LOSS_WARP || KOS) {
+        if constexpr ((LOSS == LOSS_WARP || KOS) && SPEC && !PROBE) {
+            // ---- rank sampling (T:855-899), two draws per round, judged in draw order ----
+            Philox4 r4 = {0u, 0u, 0u, 0u};
+            bool active = valid && max_sampled > 0;
+            for (int round = 0; __any_sync(LFM_FULL, active); round++) {
+                if ((round & 1) == 0)
+                    r4 = philox7((uint32_t)t, 0u, (uint32_t)(round >> 1), 0u, a.seed, 0x4c464d31u);
+                const uint32_t ra = (round & 1) ? r4.z : r4.x, rb = (round & 1) ? r4.w : r4.y;
+                const int ca = lfm_bounded(ra, (uint32_t)n_items), cb = lfm_bounded(rb, (uint32_t)n_items);
+                const bool act_b = active && sampled + 1 < max_sampled;
+                float4 qb[VPL];
+                float ba = 0.0f, bb = 0.0f;
+#pragma unroll
+                for (int v = 0; v < VPL; v++) qb[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (active) {
+#pragma unroll
+                    for (int v = 0; v < VPL; v++) q[v] = ldcg4(m.item.w + (size_t)ca * D + (sub + LPR * v) * 4);
+                    ba = __ldcg(m.item.b + ca);
+                }
+                if (act_b) {
+#pragma unroll
+                    for (int v = 0; v < VPL; v++) qb[v] = ldcg4(m.item.w + (size_t)cb * D + (sub + LPR * v) * 4);
+                    bb = __ldcg(m.item.b + cb);
+                }
+                float pa = 0.0f, pb2 = 0.0f;
+#pragma unroll
+                for (int v = 0; v < VPL; v++) { pa += dot4(u[v], q[v]); pb2 += dot4(u[v], qb[v]); }
+                const float npa = slot_sum<LPR>(pa) + cs.ub + ba;
+                const float npb = slot_sum<LPR>(pb2) + cs.ub + bb;
+                const bool va = active && npa > pp - 1.0f, vb = act_b && npb > pp - 1.0f;
+                bool ma, mb;
+                if (BITMAP) {
+                    const uint32_t* brow = a.pos_bitmap + (size_t)cur.user * a.bitmap_words;
+                    const uint32_t wa = va ? __ldg(brow + (ca >> 5)) : 0u, wb = vb ? __ldg(brow + (cb >> 5)) : 0u;
+                    ma = va && ((wa >> (ca & 31)) & 1u);
+                    mb = vb && ((wb >> (cb & 31)) & 1u);
+                } else {
+                    ma = slot_member<LPR>(a.pos.indices, cs.ps, cs.pe, cs.probe, ca, va, sub, slotmask);
+                    mb = slot_member<LPR>(a.pos.indices, cs.ps, cs.pe, cs.probe, cb, vb, sub, slotmask);
+                }
+                if (active) {
+                    sampled++;
+                    if (va && !ma) {
+                        neg_id = ca;
+                        loss = fminf((KOS ? 1.0f : cur.weight) * __ldg(a.loss_table_f + sampled), (float)LFM_MAX_LOSS);
+                    } else {
+                        if (va && sub == 0) c_rej++;
+                        if (act_b) {
+                            sampled++;
+                            if (vb && !mb) {
+                                neg_id = cb;
+                                loss = fminf((KOS ? 1.0f : cur.weight) * __ldg(a.loss_table_f + sampled), (float)LFM_MAX_LOSS);
+#pragma unroll
+                                for (int v = 0; v < VPL; v++) q[v] = qb[v];
+                            } else if (vb && sub == 0) {
+                                c_rej++;
+                            }
+                        }
+                    }
+                    active = neg_id < 0 && sampled < max_sampled;
+                }
+            }
+        } else if constexpr (LOSS == LOSS_WARP || KOS) {
             // ---- rank sampling (T:855-899): every slot draws its own candidates in lockstep ----
             Philox4 r4 = {0u, 0u, 0u, 0u};
             bool active = valid && max_sampled > 0;
@@ -706,13 +773,13 @@ FastGrid fast_grid(K kernel, int64_t warps_wanted, int64_t warps_cap) {
     return g;
 }
 
-template <int LOSS, int D, int VPL, int MINB, bool BITMAP, int KSR = 1>
+template <int LOSS, int D, int VPL, int MINB, bool BITMAP, int KSR = 1, bool SPEC = false>
 cudaError_t launch_slot_impl(const FitArgs& b, const Tuple* tp, int64_t count, cudaStream_t st) {
     constexpr int LPR = D / (4 * VPL);
     constexpr int NS = 32 / LPR;
     constexpr int BT = 256, WPB = BT / 32;  // threads / warps per block
     const size_t smem = (size_t)WPB * NS * 2 * 4 * D * sizeof(float);
-    auto kern = fast_slot_kernel<LOSS, D, VPL, MINB, BITMAP, KSR>;
+    auto kern = fast_slot_kernel<LOSS, D, VPL, MINB, BITMAP, KSR, false, SPEC>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BT, smem);
@@ -730,12 +797,12 @@ cudaError_t launch_slot_impl(const FitArgs& b, const Tuple* tp, int64_t count, c
     return cudaGetLastError();
 }
 
-template <int LOSS, int D, int VPL, int MINB, int KSR = 1>
+template <int LOSS, int D, int VPL, int MINB, int KSR = 1, bool SPEC = false>
 cudaError_t launch_slot(const FitArgs& b, const Tuple* tp, int64_t count, cudaStream_t st) {
     if constexpr (LOSS != LOSS_LOGISTIC) {
-        if (b.pos_bitmap) return launch_slot_impl<LOSS, D, VPL, MINB, true, KSR>(b, tp, count, st);
+        if (b.pos_bitmap) return launch_slot_impl<LOSS, D, VPL, MINB, true, KSR, SPEC>(b, tp, count, st);
     }
-    return launch_slot_impl<LOSS, D, VPL, MINB, false, KSR>(b, tp, count, st);
+    return launch_slot_impl<LOSS, D, VPL, MINB, false, KSR, SPEC>(b, tp, count, st);
 }
 
 // Test hook (lfm_set_probe): one warp, one interaction in flight, rand_r negatives.
@@ -755,6 +822,7 @@ cudaError_t launch_probe(const FitArgs& b, const Tuple* tp, cudaStream_t st) {
 //   4 / 5  fast_slot_kernel, one float4 per lane, 3 / 4 CTAs per SM
 //   6/7/8  fast_slot_kernel, two float4 per lane (twice the interactions per warp; d >= 32),
 //          2 / 3 / 4 CTAs per SM                                   [7 = default, fastest on C2]
+//   9/10   as 7 / 6 with two speculative candidates per slot per round (SPEC)
 // Also tried and dropped (within +-1.5 % of variant 7 once the bitmap was in): 128-thread blocks
 // at 6-8 CTAs per SM (up to 28 warps / SM), and L2 evict-first cache hints on the tuple stream
 // and the CSR probes.
@@ -800,6 +868,8 @@ cudaError_t launch_fast(const FitArgs& a, const Tuple* tuples, int64_t begin, in
         if (g_tuning == 4) return launch_slot<LOSS, DD, 1, 3>(b, tp, count, st);
         if (g_tuning == 5 || g_tuning == 0) return launch_slot<LOSS, DD, 1, 4>(b, tp, count, st);
         if constexpr (DD >= 32) {
+            if (g_tuning == 9) return launch_slot<LOSS, DD, 2, 3, 1, true>(b, tp, count, st);
+            if (g_tuning == 10) return launch_slot<LOSS, DD, 2, 2, 1, true>(b, tp, count, st);
             if (g_tuning == 6) return launch_slot<LOSS, DD, 2, 2>(b, tp, count, st);
             if (g_tuning == 8) return launch_slot<LOSS, DD, 2, 4>(b, tp, count, st);
             return launch_slot<LOSS, DD, 2, 3>(b, tp, count, st);
@@ -826,7 +896,7 @@ cudaError_t launch_fast_d(const FitArgs& a, const Tuple* tuples, int64_t begin, 
 
 extern "C" int lfm_set_tuning(int variant) {
     int old = g_tuning.load();
-    if (variant == 0 || (variant >= 4 && variant <= 8)) g_tuning.store(variant);
+    if (variant == 0 || (variant >= 4 && variant <= 10)) g_tuning.store(variant);
     return old;
 }
 

@@ -17,6 +17,8 @@
 //   update_biases T:337-391, update_features T:394-451, update T:454-534,
 //   warp_update T:537-649, regularize T:652-675, fit_logistic T:694-781,
 //   fit_warp T:784-912, fit_warp_kos T:915-1071, fit_bpr T:1074-1182.
+#include <atomic>
+
 #include "lfm_common.cuh"
 
 namespace {
@@ -453,7 +455,17 @@ __global__ void regularize_kernel(DevModel m, DevScales* scales) {
 
 }  // namespace
 
+#include "lfm_replay_fast.cuh"
+
+static std::atomic<int> g_replay_fast{1};
+extern "C" int lfm_set_replay_fast(int enabled) { return g_replay_fast.exchange(enabled ? 1 : 0); }
+
 cudaError_t lfm_launch_replay(int loss, const FitArgs& a, cudaStream_t st) {
+    if (g_replay_fast.load()) {
+        cudaError_t e = lfm_try_launch_replay_fast(loss, a, st);
+        if (e != cudaErrorNotSupported) return e;
+        cudaGetLastError();
+    }
     int d = a.model.d;
     int nk = a.nkos > 0 ? a.nkos : 1;
     size_t smem = sizeof(double) * 3 * d + sizeof(float) * 3 * (d + 1) + (sizeof(float) + sizeof(int)) * nk + 16;

@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 import scipy.sparse as sp
 
+import helpers as H
 from lightfm_b200 import LightFM
 from lightfm_b200.cross_validation import random_train_test_split
 
@@ -92,3 +93,58 @@ def test_random_train_test_split_is_a_partition():
     assert train.tocsr().multiply(test.tocsr()).nnz == 0
     with pytest.raises(ValueError):
         random_train_test_split(np.zeros((3, 3)))
+
+
+# ---- round 2: resident-plan cache keys, tier-B fixtures -------------------------------------------
+def test_resident_cache_matches_only_identical_buffers_and_hyperparameters():
+    import scipy.sparse as sp
+    from lightfm_b200.lightfm import LightFM, _ResidentCache
+    inter = H.synthetic_interactions(60, 40, 500, 1)
+    model = LightFM(loss="warp", no_components=16)
+    cache = _ResidentCache(model, inter, None, None, None)
+    cache.plan = object()          # stands in for a live plan (no GPU needed for the key logic)
+    assert cache.matches(model, inter, None, None, None)
+    # same values, different buffers: not a hit (identity of the arrays is the key)
+    clone = sp.coo_matrix((inter.data.copy(), (inter.row.copy(), inter.col.copy())), shape=inter.shape)
+    assert not cache.matches(model, clone, None, None, None)
+    # a feature matrix or weights appearing: not a hit
+    assert not cache.matches(model, inter, sp.identity(60, format="csr", dtype=np.float32), None, None)
+    # hyper-parameter change: not a hit
+    model.learning_rate = 0.1
+    assert not cache.matches(model, inter, None, None, None)
+    model.learning_rate = 0.05
+    assert cache.matches(model, inter, None, None, None)
+    # in-place edit of the interaction buffer is noticed by the strided sample
+    inter.col[0] = (inter.col[0] + 1) % 40
+    assert not cache.matches(model, inter, None, None, None)
+    cache.plan = None
+
+
+def test_model_pickles_without_device_handles():
+    import pickle
+    from lightfm_b200.lightfm import LightFM
+    model = LightFM(loss="bpr", no_components=8, random_state=3)
+    model._initialize(8, 5, 7)
+    model.__dict__["_resident_cache"] = object()   # whatever a fit left behind must not be pickled
+    clone = pickle.loads(pickle.dumps(model))
+    assert clone.__dict__.get("_resident_cache") is None
+    assert np.array_equal(clone.item_embeddings, model.item_embeddings)
+    model.__dict__["_resident_cache"] = None
+
+
+def test_tierb_band_fixture_is_consistent_with_the_generator():
+    import json
+    import os
+    path = os.path.join(H.GOLDEN_DIR, "tierb_bands.json")
+    bands = json.load(open(path))
+    assert set(bands) == set(H.TIERB)
+    for name, rec in bands.items():
+        cfg = H.TIERB[name]
+        assert rec["config"]["epochs"] == cfg["epochs"] and rec["config"].get("lr") == cfg.get("lr"), name
+        for side in ("oracle_1thread", "reference_8threads"):
+            assert len(rec["runs"][side]) == len(H.TIERB_SEEDS)
+        lo, hi = rec["band"]["auc"]
+        assert 0.5 < lo <= hi < 1.0
+    # the committed digest is the digest of what the generator produces here (C1 shape: fast)
+    fit, _, _, _ = H.tierb_problem("c1_warp")
+    assert H.data_digest(fit) == bands["c1_warp"]["digest"]

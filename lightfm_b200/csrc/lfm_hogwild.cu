@@ -298,17 +298,30 @@ __device__ __forceinline__ void hot_drain(const HotSmem& h, int slot, const FitA
     }
 }
 
-// Gather in the float4 layout with the row loads of up to four features in flight at a time
+// A row's feature list as the lanes hold it after a gather (feature i of the row on lane i):
+// reused by the scatter of the same row, which then needs no index loads of its own.
+struct FeatRow {
+    int ft;     // feature (embedding row) id
+    float fw;   // feature weight
+    int hs;     // hot slot of that embedding row, or -1
+    int cnt;    // number of features (<= 32), or -1 when the row was too long to keep
+};
+
+#define FB 10  // feature rows in flight per batch (C3: identity + up to 8 tags + slack)
+
+// Gather in the float4 layout with the row loads of up to FB features in flight at a time
 // (the generic gather walks the features one dependent round trip after the other).
 template <int KPL>
-__device__ __forceinline__ void gather_b(const DevCsr& f, const DevTable& t, int d, int row,
-                                         Repr<KPL>& r, int lane) {
+__device__ __forceinline__ void gather_b(const DevCsr& f, const DevTable& t, const int32_t* __restrict__ hot_slot,
+                                         int d, int row, Repr<KPL>& r, FeatRow& fr, int lane) {
     constexpr int NCH = KPL / 4;
 #pragma unroll
     for (int k = 0; k < KPL; k++) r.v[k] = 0.0f;
     r.b = 0.0f;
     const int d4 = d >> 2;
     if (f.identity) {
+        fr.ft = row; fr.fw = 1.0f; fr.cnt = 1;
+        fr.hs = (hot_slot != nullptr && lane == 0) ? __ldg(hot_slot + row) : -1;
 #pragma unroll
         for (int j = 0; j < NCH; j++) {
             const int c = lane + 32 * j;
@@ -321,17 +334,24 @@ __device__ __forceinline__ void gather_b(const DevCsr& f, const DevTable& t, int
         return;
     }
     const int start = __ldg(f.indptr + row), stop = __ldg(f.indptr + row + 1);
+    fr.cnt = (stop - start <= 32) ? stop - start : -1;
+    fr.ft = 0; fr.fw = 0.0f; fr.hs = -1;
     float bsum = 0.0f;
     for (int base = start; base < stop; base += 32) {
         const int cnt = min(32, stop - base);
         const int my_ft = lane < cnt ? __ldg(f.indices + base + lane) : 0;
         const float my_fw = lane < cnt ? __ldg(f.data + base + lane) : 0.0f;
-        if (lane < cnt) bsum = fmaf(my_fw, __ldcg(t.b + my_ft), bsum);
-        for (int i0 = 0; i0 < cnt; i0 += 4) {
-            float4 x[4][NCH];
-            float w[4];
+        if (lane < cnt) {
+            bsum = fmaf(my_fw, __ldcg(t.b + my_ft), bsum);
+            if (hot_slot != nullptr) fr.hs = __ldg(hot_slot + my_ft);
+        }
+        fr.ft = my_ft; fr.fw = my_fw;
+#pragma unroll 1
+        for (int i0 = 0; i0 < cnt; i0 += FB) {
+            float4 x[FB][NCH];
+            float w[FB];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
+            for (int k = 0; k < FB; k++) {
                 const int i = i0 + k;
                 const int ft = __shfl_sync(LFM_FULL, my_ft, i & 31);
                 w[k] = __shfl_sync(LFM_FULL, my_fw, i & 31);
@@ -344,7 +364,7 @@ __device__ __forceinline__ void gather_b(const DevCsr& f, const DevTable& t, int
                 }
             }
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
+            for (int k = 0; k < FB; k++) {
 #pragma unroll
                 for (int j = 0; j < NCH; j++) {
                     r.v[4 * j] = fmaf(w[k], x[k][j].x, r.v[4 * j]);
@@ -358,27 +378,89 @@ __device__ __forceinline__ void gather_b(const DevCsr& f, const DevTable& t, int
     r.b = lfm_warp_sum(bsum);
 }
 
-// Adagrad scatter (alpha == 0) in the float4 layout: accumulator rows of up to four features
-// are fetched together; rows with a hot slot go to the CTA's shared-memory accumulator.
+// One feature row's share of an Adagrad update (alpha == 0), accumulator chunk already in g0.
+// Hot rows go to the CTA's shared-memory accumulator under the slot lock, everything else (and
+// a hot row whose lock is busy) straight to L2.
+template <int KPL>
+__device__ __forceinline__ void apply_row(DevTable& t, const HotSmem& h, const DevModel& m, int ft, float fw, int hs,
+                                          const float4 (&g0)[KPL / 4], const float (&grad)[KPL], float bgrad,
+                                          int lane) {
+    constexpr int NCH = KPL / 4;
+    const int d = m.d, d4 = d >> 2;
+    const float lr = m.lr;
+    if (hs >= 0) {
+        int* lock = h.locks + hs;
+        if (hot_lock(lock, lane)) {
+            float4* sb = h.acc + (size_t)hs * h.stride;
+#pragma unroll
+            for (int j = 0; j < NCH; j++) {
+                const int c = lane + 32 * j;
+                if (c < d4) {
+                    const float gx = grad[4 * j] * fw, gy = grad[4 * j + 1] * fw, gz = grad[4 * j + 2] * fw,
+                                gw = grad[4 * j + 3] * fw;
+                    float4 aw = sb[c], ag = sb[d4 + c];
+                    aw.x -= lr * rsqrt_ftz(g0[j].x) * gx; aw.y -= lr * rsqrt_ftz(g0[j].y) * gy;
+                    aw.z -= lr * rsqrt_ftz(g0[j].z) * gz; aw.w -= lr * rsqrt_ftz(g0[j].w) * gw;
+                    ag.x = fmaf(gx, gx, ag.x); ag.y = fmaf(gy, gy, ag.y);
+                    ag.z = fmaf(gz, gz, ag.z); ag.w = fmaf(gw, gw, ag.w);
+                    sb[c] = aw;
+                    sb[d4 + c] = ag;
+                }
+            }
+            if (lane == 0) {
+                const float g = bgrad * fw;
+                const float bg0 = __ldcg(t.bg + ft);
+                float4 ab = sb[2 * d4];
+                ab.x -= lr * rsqrt_ftz(bg0) * g;
+                ab.y = fmaf(g, g, ab.y);
+                sb[2 * d4] = ab;
+            }
+            hot_unlock(lock, lane);
+            return;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NCH; j++) {
+        const int c = lane + 32 * j;
+        if (c < d4) {
+            const float gx = grad[4 * j] * fw, gy = grad[4 * j + 1] * fw, gz = grad[4 * j + 2] * fw,
+                        gw = grad[4 * j + 3] * fw;
+            const size_t o = (size_t)ft * d + c * 4;
+            red_add_v4(t.w + o, -lr * rsqrt_ftz(g0[j].x) * gx, -lr * rsqrt_ftz(g0[j].y) * gy,
+                       -lr * rsqrt_ftz(g0[j].z) * gz, -lr * rsqrt_ftz(g0[j].w) * gw);
+            red_add_v4(t.g + o, gx * gx, gy * gy, gz * gz, gw * gw);
+        }
+    }
+    if (hs >= 0 && lane == 0) {  // slot busy: its bias goes the direct way as well
+        const float g = bgrad * fw;
+        const float bg0 = __ldcg(t.bg + ft);
+        red_add(t.b + ft, -lr * rsqrt_ftz(bg0) * g);
+        red_add(t.bg + ft, g * g);
+    }
+}
+
+// Adagrad scatter (alpha == 0) in the float4 layout: the accumulator rows of up to FB features
+// are fetched together; `fr` (from the gather of the same row) saves the index loads.
 template <int KPL>
 __device__ __forceinline__ void scatter_b(const DevCsr& f, DevTable& t, const int32_t* __restrict__ hot_slot,
-                                          const HotSmem& h, const DevModel& m, int row,
+                                          const HotSmem& h, const DevModel& m, int row, const FeatRow& fr,
                                           const float (&grad)[KPL], float bgrad, int lane) {
     constexpr int NCH = KPL / 4;
     const int d = m.d, d4 = d >> 2;
     const float lr = m.lr;
-    int start, stop;
-    if (f.identity) { start = 0; stop = 1; }
-    else { start = __ldg(f.indptr + row); stop = __ldg(f.indptr + row + 1); }
+    int start = 0, stop = fr.cnt;
+    const bool reuse = fr.cnt >= 0;
+    if (!reuse) { start = __ldg(f.indptr + row); stop = __ldg(f.indptr + row + 1); }
     for (int base = start; base < stop; base += 32) {
         const int cnt = min(32, stop - base);
-        int my_ft = row;
-        float my_fw = 1.0f;
-        if (!f.identity) {
+        int my_ft = fr.ft, my_hs = fr.hs;
+        float my_fw = fr.fw;
+        if (!reuse) {
             my_ft = lane < cnt ? __ldg(f.indices + base + lane) : 0;
             my_fw = lane < cnt ? __ldg(f.data + base + lane) : 0.0f;
+            my_hs = (hot_slot != nullptr && lane < cnt) ? __ldg(hot_slot + my_ft) : -1;
         }
-        const int my_hs = (hot_slot != nullptr && lane < cnt) ? __ldg(hot_slot + my_ft) : -1;
+        if (lane >= cnt) my_hs = -1;
         // biases of the rows without a slot: one feature per lane, all in flight together
         if (lane < cnt && my_hs < 0) {
             const float g = bgrad * my_fw;
@@ -386,78 +468,28 @@ __device__ __forceinline__ void scatter_b(const DevCsr& f, DevTable& t, const in
             red_add(t.b + my_ft, -lr * rsqrt_ftz(g0) * g);
             red_add(t.bg + my_ft, g * g);
         }
-        for (int i0 = 0; i0 < cnt; i0 += 4) {
-            float4 g0[4][NCH];
-            int ft[4], hs[4];
-            float fw[4];
+#pragma unroll 1
+        for (int i0 = 0; i0 < cnt; i0 += FB) {
+            float4 g0[FB][NCH];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
+            for (int k = 0; k < FB; k++) {
                 const int i = i0 + k;
-                ft[k] = __shfl_sync(LFM_FULL, my_ft, i & 31);
-                fw[k] = __shfl_sync(LFM_FULL, my_fw, i & 31);
-                hs[k] = __shfl_sync(LFM_FULL, my_hs, i & 31);
+                const int ft = __shfl_sync(LFM_FULL, my_ft, i & 31);
 #pragma unroll
                 for (int j = 0; j < NCH; j++) {
                     const int c = lane + 32 * j;
-                    g0[k][j] = (i < cnt && c < d4) ? ldcg4(t.g + (size_t)ft[k] * d + c * 4)
+                    g0[k][j] = (i < cnt && c < d4) ? ldcg4(t.g + (size_t)ft * d + c * 4)
                                                    : make_float4(1.f, 1.f, 1.f, 1.f);
                 }
             }
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if (i0 + k >= cnt) break;  // warp-uniform
-                bool in_smem = false;
-                if (hs[k] >= 0) {
-                    int* lock = h.locks + hs[k];
-                    if (hot_lock(lock, lane)) {
-                        float4* sb = h.acc + (size_t)hs[k] * h.stride;
-#pragma unroll
-                        for (int j = 0; j < NCH; j++) {
-                            const int c = lane + 32 * j;
-                            if (c < d4) {
-                                const float gx = grad[4 * j] * fw[k], gy = grad[4 * j + 1] * fw[k],
-                                            gz = grad[4 * j + 2] * fw[k], gw = grad[4 * j + 3] * fw[k];
-                                float4 aw = sb[c], ag = sb[d4 + c];
-                                aw.x -= lr * rsqrt_ftz(g0[k][j].x) * gx; aw.y -= lr * rsqrt_ftz(g0[k][j].y) * gy;
-                                aw.z -= lr * rsqrt_ftz(g0[k][j].z) * gz; aw.w -= lr * rsqrt_ftz(g0[k][j].w) * gw;
-                                ag.x = fmaf(gx, gx, ag.x); ag.y = fmaf(gy, gy, ag.y);
-                                ag.z = fmaf(gz, gz, ag.z); ag.w = fmaf(gw, gw, ag.w);
-                                sb[c] = aw;
-                                sb[d4 + c] = ag;
-                            }
-                        }
-                        if (lane == 0) {
-                            const float g = bgrad * fw[k];
-                            const float bg0 = __ldcg(t.bg + ft[k]);
-                            float4 ab = sb[2 * d4];
-                            ab.x -= lr * rsqrt_ftz(bg0) * g;
-                            ab.y = fmaf(g, g, ab.y);
-                            sb[2 * d4] = ab;
-                        }
-                        hot_unlock(lock, lane);
-                        in_smem = true;
-                    }
-                }
-                if (!in_smem) {
-#pragma unroll
-                    for (int j = 0; j < NCH; j++) {
-                        const int c = lane + 32 * j;
-                        if (c < d4) {
-                            const float gx = grad[4 * j] * fw[k], gy = grad[4 * j + 1] * fw[k],
-                                        gz = grad[4 * j + 2] * fw[k], gw = grad[4 * j + 3] * fw[k];
-                            const size_t o = (size_t)ft[k] * d + c * 4;
-                            red_add_v4(t.w + o, -lr * rsqrt_ftz(g0[k][j].x) * gx, -lr * rsqrt_ftz(g0[k][j].y) * gy,
-                                       -lr * rsqrt_ftz(g0[k][j].z) * gz, -lr * rsqrt_ftz(g0[k][j].w) * gw);
-                            red_add_v4(t.g + o, gx * gx, gy * gy, gz * gz, gw * gw);
-                        }
-                    }
-                    if (hs[k] >= 0 && lane == 0) {  // slot busy: its bias goes the direct way as well
-                        const float g = bgrad * fw[k];
-                        const float bg0 = __ldcg(t.bg + ft[k]);
-                        red_add(t.b + ft[k], -lr * rsqrt_ftz(bg0) * g);
-                        red_add(t.bg + ft[k], g * g);
-                    }
-                }
+            for (int k = 0; k < FB; k++) {
+                const int i = i0 + k;
+                if (i >= cnt) break;  // warp-uniform
+                const int ft = __shfl_sync(LFM_FULL, my_ft, i & 31);
+                const float fw = __shfl_sync(LFM_FULL, my_fw, i & 31);
+                const int hs = __shfl_sync(LFM_FULL, my_hs, i & 31);
+                apply_row<KPL>(t, h, m, ft, fw, hs, g0[k], grad, bgrad, lane);
             }
         }
     }
@@ -501,15 +533,16 @@ __global__ void __launch_bounds__(HOT ? 512 : 256) hogwild_kernel(FitArgs a, con
         rs.base_u = __ldcg(&a.scales->user_scale);
     }
 
-#define GATHER(F, T, ROW, SCALE, R)                                          \
+    FeatRow fr_u = {0, 0.f, -1, -1}, fr_p = fr_u, fr_q = fr_u;  // feature lists kept from the gathers (HOT)
+#define GATHER(F, T, SLOTS, ROW, SCALE, R, FR)                               \
     do {                                                                     \
-        if constexpr (HOT) gather_b<KPL>(F, T, d, ROW, R, lane);             \
+        if constexpr (HOT) gather_b<KPL>(F, T, SLOTS, d, ROW, R, FR, lane);  \
         else gather<KPL, VW>(F, T, d, ROW, SCALE, R, lane);                  \
     } while (0)
-#define SCATTER(F, T, SLOTS, ROW, GRAD, BGRAD, ALPHA, NNZ)                                        \
-    do {                                                                                          \
-        if constexpr (HOT) { scatter_b<KPL>(F, T, SLOTS, hsm, m, ROW, GRAD, BGRAD, lane); NNZ = 0; } \
-        else lrsum += scatter<KPL, VW, ADADELTA>(F, T, m, ROW, GRAD, BGRAD, ALPHA, lane, NNZ);    \
+#define SCATTER(F, T, SLOTS, ROW, FR, GRAD, BGRAD, ALPHA, NNZ)                                        \
+    do {                                                                                              \
+        if constexpr (HOT) { scatter_b<KPL>(F, T, SLOTS, hsm, m, ROW, FR, GRAD, BGRAD, lane); NNZ = 0; } \
+        else lrsum += scatter<KPL, VW, ADADELTA>(F, T, m, ROW, GRAD, BGRAD, ALPHA, lane, NNZ);        \
     } while (0)
     for (int64_t tl = warp; tl < a.n; tl += nwarps) {
         if constexpr (HOT) {
@@ -533,21 +566,21 @@ __global__ void __launch_bounds__(HOT ? 512 : 256) hogwild_kernel(FitArgs a, con
         }
         const int user = tp.user;
         Repr<KPL> u, p, q;
-        GATHER(a.usf, m.user, user, user_scale, u);
+        GATHER(a.usf, m.user, a.hot_slot_user, user, user_scale, u, fr_u);
         float lrsum = 0.0f;
         int nnz_total = 0;
         bool updated = false;
 
         if (LOSS == LOSS_LOGISTIC) {
-            GATHER(a.itf, m.item, tp.item, item_scale, p);
+            GATHER(a.itf, m.item, a.hot_slot_item, tp.item, item_scale, p, fr_p);
             float pred = 1.0f / (1.0f + __expf(-dot<KPL>(u, p)));
             float loss = tp.weight * (pred - (tp.y > 0 ? 1.0f : 0.0f));
             float gi[KPL], gu[KPL];
 #pragma unroll
             for (int k = 0; k < KPL; k++) { gi[k] = loss * u.v[k]; gu[k] = loss * p.v[k]; }
             int n1, n2;
-            SCATTER(a.itf, m.item, a.hot_slot_item, tp.item, gi, loss, alpha_i, n1);
-            SCATTER(a.usf, m.user, a.hot_slot_user, user, gu, loss, alpha_u, n2);
+            SCATTER(a.itf, m.item, a.hot_slot_item, tp.item, fr_p, gi, loss, alpha_i, n1);
+            SCATTER(a.usf, m.user, a.hot_slot_user, user, fr_u, gu, loss, alpha_u, n2);
             nnz_total = n1 + n2;
             updated = true;
             c_pos++; c_upd++;
@@ -575,7 +608,7 @@ __global__ void __launch_bounds__(HOT ? 512 : 256) hogwild_kernel(FitArgs a, con
                 float my_val = 0.0f;
                 for (int j = 0; j < no_pos; j++) {
                     int sid = __ldg(a.pos.indices + ps + lfm_bounded(next_u32(), (uint32_t)(pe - ps)));
-                    GATHER(a.itf, m.item, sid, item_scale, p);
+                    GATHER(a.itf, m.item, a.hot_slot_item, sid, item_scale, p, fr_p);
                     float s = dot<KPL>(u, p);
                     if (lane == j) { my_idx = sid; my_val = s; }
                 }
@@ -591,10 +624,10 @@ __global__ void __launch_bounds__(HOT ? 512 : 256) hogwild_kernel(FitArgs a, con
                 if (src < 0) src = 0;  // NaN scores: fall back to the first sample
                 pos_id = __shfl_sync(LFM_FULL, my_idx, src);
                 pp = __shfl_sync(LFM_FULL, my_val, src);
-                GATHER(a.itf, m.item, pos_id, item_scale, p);
+                GATHER(a.itf, m.item, a.hot_slot_item, pos_id, item_scale, p, fr_p);
                 c_pos++;
             } else {
-                GATHER(a.itf, m.item, pos_id, item_scale, p);
+                GATHER(a.itf, m.item, a.hot_slot_item, pos_id, item_scale, p, fr_p);
                 pp = dot<KPL>(u, p);
                 c_pos++;
             }
@@ -611,7 +644,7 @@ __global__ void __launch_bounds__(HOT ? 512 : 256) hogwild_kernel(FitArgs a, con
                     if (!lfm_warp_member(a.pos.indices, ps, pe, neg_id, lane)) break;
                     c_rej++;
                 } while (tries < 256);
-                GATHER(a.itf, m.item, neg_id, item_scale, q);
+                GATHER(a.itf, m.item, a.hot_slot_item, neg_id, item_scale, q, fr_q);
                 float np = dot<KPL>(u, q);
                 loss = tp.weight * (1.0f - 1.0f / (1.0f + __expf(-(pp - np))));
                 updated = true;
@@ -620,7 +653,7 @@ __global__ void __launch_bounds__(HOT ? 512 : 256) hogwild_kernel(FitArgs a, con
                 while (sampled < m.max_sampled) {
                     sampled++;
                     int cand = lfm_bounded(next_u32(), (uint32_t)n_items);
-                    GATHER(a.itf, m.item, cand, item_scale, q);
+                    GATHER(a.itf, m.item, a.hot_slot_item, cand, item_scale, q, fr_q);
                     float np = dot<KPL>(u, q);
                     c_neg++;
                     if (np > pp - 1.0f) {
@@ -643,9 +676,9 @@ __global__ void __launch_bounds__(HOT ? 512 : 256) hogwild_kernel(FitArgs a, con
                     gu[k] = loss * (q.v[k] - p.v[k]);
                 }
                 int n1, n2, n3;
-                SCATTER(a.itf, m.item, a.hot_slot_item, pos_id, gp, -loss, alpha_i, n1);
-                SCATTER(a.itf, m.item, a.hot_slot_item, neg_id, gn, loss, alpha_i, n2);
-                SCATTER(a.usf, m.user, a.hot_slot_user, user, gu, loss, alpha_u, n3);
+                SCATTER(a.itf, m.item, a.hot_slot_item, pos_id, fr_p, gp, -loss, alpha_i, n1);
+                SCATTER(a.itf, m.item, a.hot_slot_item, neg_id, fr_q, gn, loss, alpha_i, n2);
+                SCATTER(a.usf, m.user, a.hot_slot_user, user, fr_u, gu, loss, alpha_u, n3);
                 nnz_total = n1 + n2 + n3;
                 c_upd++;
             }

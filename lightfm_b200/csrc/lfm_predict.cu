@@ -433,6 +433,9 @@ __global__ void __launch_bounds__(256) topk_select_kernel(const float* __restric
         const uint32_t thr = s_prefix;      // key of the k-th largest score
         const uint32_t need_ties = s_need;  // how many keys == thr belong to the top k
         if (threadIdx.x == 0) { s_count = 0u; s_ties = 0u; }
+        // every slot starts as "no item" (fewer than k items can be scorable: n_items < k, NaN
+        // scores, excluded items), and sorts behind every real winner
+        for (int i = threadIdx.x; i < TOPK_MAX; i += blockDim.x) { win_key[i] = 0u; win_idx[i] = 0x7fffffff; }
         __syncthreads();
         // ---- winners strictly above the threshold (any order), then the ties in ascending item order
         for (int i = threadIdx.x; i < n_items; i += blockDim.x) {
@@ -456,7 +459,7 @@ __global__ void __launch_bounds__(256) topk_select_kernel(const float* __restric
             uint32_t before = s_ties;
             for (int ww = 0; ww < w; ww++) before += warp_cnt[ww];
             const uint32_t mine = before + __popc(bal & ((1u << lane) - 1u));
-            if (tie && mine < need_ties) {
+            if (tie && mine < need_ties && n_above + mine < (uint32_t)k && thr != 0u) {
                 win_key[n_above + mine] = thr;
                 win_idx[n_above + mine] = i;
             }
@@ -471,7 +474,6 @@ __global__ void __launch_bounds__(256) topk_select_kernel(const float* __restric
         // ---- sort the k winners: key descending, item id ascending
         int p2 = 2;
         while (p2 < k) p2 <<= 1;
-        for (int i = k + threadIdx.x; i < p2; i += blockDim.x) { win_key[i] = 0u; win_idx[i] = 0x7fffffff; }
         __syncthreads();
         for (int kk = 2; kk <= p2; kk <<= 1)
             for (int j = kk >> 1; j > 0; j >>= 1) {

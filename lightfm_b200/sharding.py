@@ -13,9 +13,14 @@ The path shards on ONE axis and has ONE exchange per epoch:
 Exchange: the replicated table's epoch delta is all-reduced (NCCL over NVLink):
 ``W <- W0 + sum_g (W_g - W0)``, same for the Adagrad accumulators and biases.
 
+Feature matrices (third bullet): with non-identity features on the SHARDED side
+(item tags under ``axis="item"``) a feature row can be touched from every shard, so the whole
+feature-embedding table of that side joins the replicated block -- every rank keeps all of its
+rows, trains on its own entities' rows of the feature matrix, and both tables' deltas are
+all-reduced (rows only one shard touches contribute zeros from the others, so the sum is exact).
+
 Everything here is host-side index work (numpy) plus the collective; the kernels are the
-single-GPU ones running on local ids.  Identity features only (feature rows shared across
-shards would have to join the replicated block).
+single-GPU ones running on local ids.
 """
 import numpy as np
 import scipy.sparse as sp
@@ -153,10 +158,13 @@ class ShardedTrainer(object):
         trainer.fit_epochs(10)
         trainer.gather()          # every rank's model arrays now hold the full trained state
 
-    Identity features only (see module docstring).
+    ``item_features`` / ``user_features`` (optional scipy matrices, rows = global entity ids):
+    a feature matrix on the sharded side is cut to this rank's entities and its embedding table
+    is kept whole and exchanged like the replicated side's (module docstring).
     """
 
-    def __init__(self, model, interactions, axis="item", sample_weight=None, group=None, device=None):
+    def __init__(self, model, interactions, axis="item", sample_weight=None, group=None, device=None,
+                 item_features=None, user_features=None):
         import torch
         import torch.distributed as dist
         from . import _lightfm_fast as native
@@ -174,13 +182,27 @@ class ShardedTrainer(object):
             coo.data = coo.data.astype(np.float32)
         self.shape = coo.shape
         n_users, n_items = coo.shape
+        feats = {"item": item_features, "user": user_features}
+        for k, f in feats.items():
+            if f is not None:
+                f = f.tocsr().astype(np.float32)
+                f.sort_indices()
+                feats[k] = f
         if model.item_embeddings is None:
-            model._initialize(model.no_components, n_items, n_users)
+            model._initialize(model.no_components,
+                              feats["item"].shape[1] if feats["item"] is not None else n_items,
+                              feats["user"].shape[1] if feats["user"] is not None else n_users)
         local, weight, positives, self.smap = partition(coo, sample_weight, axis, self.rank, self.world)
         if weight is None:
             weight = local.data if np.array_equiv(local.data, 1.0) else np.ones_like(local.data)
         self._global = {k: getattr(model, k) for k in _STATE_NAMES}
-        self.local_state = slice_state(self._global, axis, self.smap)
+        side_name = "item" if axis == "item" else "user"
+        # a feature matrix on the sharded side: its embedding table is not cut (shared rows)
+        self.sliced = feats[side_name] is None
+        if self.sliced:
+            self.local_state = slice_state(self._global, axis, self.smap)
+        else:
+            self.local_state = {k: v.copy() for k, v in self._global.items()}
         st = self.local_state
         self._holder = native.FastLightFM(
             *[st[k] for k in _STATE_NAMES], model.no_components, 0, model.learning_rate, model.rho,
@@ -188,29 +210,39 @@ class ShardedTrainer(object):
         lu, li = local.shape
         kos = model.loss == "warp-kos"
         self._keep = (local, weight, positives)
+        def local_features(name, n_local):
+            f = feats[name]
+            if f is None:
+                return sp.identity(n_local, dtype=np.float32, format="csr")
+            if name == side_name:                      # rows of this rank's entities, all feature columns
+                f = f[self.smap.global_ids]
+                f.sort_indices()
+            return f
+        self._features = (local_features("item", li), local_features("user", lu))
         self.plan = native.ResidentPlan(
-            model.loss, native.CSRMatrix(sp.identity(li, dtype=np.float32, format="csr")),
-            native.CSRMatrix(sp.identity(lu, dtype=np.float32, format="csr")),
+            model.loss, native.CSRMatrix(self._features[0]), native.CSRMatrix(self._features[1]),
             native.CSRMatrix(positives) if model.loss != "logistic" else None,
             np.ascontiguousarray(local.row), None if kos else np.ascontiguousarray(local.col),
             None if kos else local.data, None if kos else weight, self._holder,
             model.item_alpha, model.user_alpha, model.k, model.n)
         if axis == "item":
             self.plan.set_global_items(n_items)
-        self.replicated_side = 1 if axis == "item" else 0   # lfm_plan_delta_* side: 0 item, 1 user
+        # lfm_plan_delta_* sides to exchange (0 item, 1 user): the replicated table, plus the sharded
+        # side's whole feature table when it has shared rows
+        self.exchange_sides = [1 if axis == "item" else 0] + ([] if self.sliced else [0 if axis == "item" else 1])
         self.local_interactions = local.nnz
         self.last_counters = None
 
     def epoch(self, seed, num_threads=8):
         """One local epoch + the delta all-reduce of the replicated table."""
-        side = self.replicated_side
-        begin_ms = self.plan.delta_begin(side) if self.world > 1 else 0.0
+        begin_ms = sum(self.plan.delta_begin(side) for side in self.exchange_sides) if self.world > 1 else 0.0
         c = self.plan.epoch(seed=(int(seed) * 977 + self.rank) & 0xFFFFFFFF, num_threads=max(2, num_threads))
-        c["allreduce_ms"] = c["exchange_ms"] = 0.0
+        c["allreduce_ms"], c["exchange_ms"] = 0.0, begin_ms
         if self.world > 1:
-            t = exchange_replicated(self.plan, side, self.device, self.group, self.world)
-            c["allreduce_ms"] = t["allreduce_ms"]
-            c["exchange_ms"] = begin_ms + t["make_ms"] + t["allreduce_ms"] + t["apply_ms"]
+            for side in self.exchange_sides:
+                t = exchange_replicated(self.plan, side, self.device, self.group, self.world)
+                c["allreduce_ms"] += t["allreduce_ms"]
+                c["exchange_ms"] += t["make_ms"] + t["allreduce_ms"] + t["apply_ms"]
         self.last_counters = c
         return c
 
@@ -226,6 +258,10 @@ class ShardedTrainer(object):
         import torch
         import torch.distributed as dist
         self.plan.download()
+        if not self.sliced:      # both tables are whole and identical on every rank after the exchange
+            for k, v in self.local_state.items():
+                self._global[k][...] = v
+            return self.model
         merge_state(self._global, self.local_state, self.axis, self.smap)
         if self.world > 1:
             side = "item" if self.axis == "item" else "user"

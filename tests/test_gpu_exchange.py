@@ -124,6 +124,18 @@ WORKER = textwrap.dedent('''
         tr.close()
         arr = {k: getattr(model, k) for k in H.MODEL_ARRAYS}
         out[axis] = H.eval_subset(arr, train, test, users)
+    # item features [I | tags] under item sharding: the tag rows are shared by every shard, so the
+    # whole item-feature table joins the exchanged block (SURVEY 8(e), third bullet)
+    itf = H.tag_features(2000, 100, 4, seed=2)
+    model = LightFM(loss="warp", no_components=32, random_state=0)
+    tr = ShardedTrainer(model, train, axis="item", item_features=itf)
+    tr.fit_epochs(5)
+    tr.gather()
+    tr.close()
+    rep = {"item_embeddings": np.asarray(itf @ model.item_embeddings),
+           "item_biases": np.asarray(itf @ model.item_biases).ravel(),
+           "user_embeddings": model.user_embeddings, "user_biases": model.user_biases}
+    out["item_features"] = H.eval_subset(rep, train, test, users)
     if rank == 0:
         print("RESULT " + json.dumps(out))
     dist.barrier(); dist.destroy_process_group()
@@ -151,6 +163,14 @@ def test_two_rank_sharded_fit_matches_single_gpu_quality(tmp_path):
     model = LightFM(loss="warp", no_components=32, random_state=0)
     model.fit(train, epochs=5, num_threads=8)
     single = H.eval_subset({k: getattr(model, k) for k in H.MODEL_ARRAYS}, train, test, users)
-    print("single GPU p@10 / auc:", single, " 2-rank sharded:", sharded)
+    itf = H.tag_features(2000, 100, 4, seed=2)
+    model = LightFM(loss="warp", no_components=32, random_state=0)
+    model.fit(train, item_features=itf, epochs=5, num_threads=8)
+    rep = {"item_embeddings": np.asarray(itf @ model.item_embeddings),
+           "item_biases": np.asarray(itf @ model.item_biases).ravel(),
+           "user_embeddings": model.user_embeddings, "user_biases": model.user_biases}
+    single_f = H.eval_subset(rep, train, test, users)
+    print("single GPU p@10 / auc:", single, "with item features:", single_f, " 2-rank sharded:", sharded)
     for axis in ("item", "user"):
         assert abs(sharded[axis][1] - single[1]) < 0.02, (axis, sharded, single)
+    assert abs(sharded["item_features"][1] - single_f[1]) < 0.02, (sharded, single_f)

@@ -144,6 +144,10 @@ int lfm_set_hot_rows(int enabled);
 /* 0: always use the general replay kernel (the prefetching WARP replay kernel is the default where
  * it applies: identity features, adagrad, alpha == 0); both are bit-equal to the oracle. */
 int lfm_set_replay_fast(int enabled);
+/* Hogwild slot kernels: 1 (default) = the Adagrad accumulator update is an atomic add that returns
+ * the old value and the step is scaled by it (every earlier update of the element is seen, whatever
+ * is in flight); 0 = read-then-reduce (round-1 behaviour). */
+int lfm_set_atomic_accumulators(int enabled);
 /* 1: run the slot kernels as ONE warp with ONE interaction in flight and the reference's rand_r
  * negatives, so that only their arithmetic differs from the oracle (tests/test_gpu_probe.py). */
 int lfm_set_probe(int enabled);

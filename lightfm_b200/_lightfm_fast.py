@@ -86,6 +86,12 @@ def set_probe(enabled):
     return _lib.lfm_set_probe(int(bool(enabled)))
 
 
+def set_atomic_accumulators(enabled):
+    """Hogwild slot kernels: scale every Adagrad step by the accumulator value returned by an atomic
+    add (default on) instead of a value read earlier (round-1 behaviour)."""
+    return _lib.lfm_set_atomic_accumulators(int(bool(enabled)))
+
+
 def set_replay_fast(enabled):
     """Replay mode: use the prefetching WARP kernel where it applies (default on; both bit-equal)."""
     return _lib.lfm_set_replay_fast(int(bool(enabled)))

@@ -190,6 +190,17 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 __device__ __forceinline__ void red_add(float* addr, float a) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
 }
+// The same reduction WITH the old value returned (ATOMG.ADD.F32x4): an Adagrad step that adds its
+// squared gradient this way reads an accumulator that already contains every earlier update of
+// that element, however many interactions are in flight.
+__device__ __forceinline__ float4 atom_add_v4(float* addr, float a, float b, float c, float d) {
+    float4 r;
+    asm volatile("atom.global.add.v4.f32 {%0, %1, %2, %3}, [%4], {%5, %6, %7, %8};"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+                 : "memory");
+    return r;
+}
 // L2-coherent vector load (ld.global.cg): tables are updated concurrently by other SMs.
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg((const float4*)p); }
 // G >= 1 under adagrad (starts at 1, only grows): no denormals, so the bare approximation is safe

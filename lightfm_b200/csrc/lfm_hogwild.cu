@@ -172,16 +172,16 @@ __device__ __forceinline__ float hstep(float* w, float* G, float* M, float fw, f
         __stcg(M, m1);
         __stcg(w, w1);
     } else {
-        float g0 = __ldcg(G);
-        llr = m.lr * rsqrtf(g0);
+        // the accumulator as every earlier update left it (atomic add with return), then the step
         float gw = grad * fw;
+        float g0 = atomicAdd(G, gw * gw);
+        llr = m.lr * rsqrtf(g0);
         float delta = -llr * gw;
         if (alpha != 0.0f) {
             float w0 = __ldcg(w);
             delta += (w0 + delta) * (alpha * llr);
         }
         atomicAdd(w, delta);
-        atomicAdd(G, gw * gw);
     }
     return llr;
 }
@@ -206,12 +206,11 @@ __device__ __forceinline__ float scatter(const DevCsr& f, DevTable& t, const Dev
             for (int j = 0; j < KPL / 4; j++) {
                 int c = (lane + 32 * j) * 4;
                 if (c < d) {
-                    const float4 g0 = ldcg4(t.g + o + c);
                     const float gx = grad[4 * j] * fw, gy = grad[4 * j + 1] * fw, gz = grad[4 * j + 2] * fw,
                                 gw = grad[4 * j + 3] * fw;
+                    const float4 g0 = atom_add_v4(t.g + o + c, gx * gx, gy * gy, gz * gz, gw * gw);
                     red_add_v4(t.w + o + c, -m.lr * rsqrt_ftz(g0.x) * gx, -m.lr * rsqrt_ftz(g0.y) * gy,
                                -m.lr * rsqrt_ftz(g0.z) * gz, -m.lr * rsqrt_ftz(g0.w) * gw);
-                    red_add_v4(t.g + o + c, gx * gx, gy * gy, gz * gz, gw * gw);
                 }
             }
         } else {
@@ -380,36 +379,32 @@ __device__ __forceinline__ void gather_b(const DevCsr& f, const DevTable& t, con
 
 // One feature row's share of an Adagrad update (alpha == 0), accumulator chunk already in g0.
 // Hot rows go to the CTA's shared-memory accumulator under the slot lock, everything else (and
-// a hot row whose lock is busy) straight to L2.
-template <int KPL>
-__device__ __forceinline__ void apply_row(DevTable& t, const HotSmem& h, const DevModel& m, int ft, float fw, int hs,
-                                          const float4 (&g0)[KPL / 4], const float (&grad)[KPL], float bgrad,
-                                          int lane) {
-    constexpr int NCH = KPL / 4;
-    const int d = m.d, d4 = d >> 2;
-    const float lr = m.lr;
+// a hot row whose lock is busy) straight to L2.  One float4 chunk per lane (d <= 128); arguments
+// by value so that they stay in registers across the call.
+// (not inlined: it is called from FB unrolled sites per scatter, and the kernel's instruction
+//  footprint was already costing instruction-cache misses: profiles/r2_ncu_c3_hot_v1_summary.txt)
+__device__ __noinline__ void apply_row(float* tw, float* tg, float* tb, float* tbg, float4* hacc, int* hlocks,
+                                       int hstride, int d, float lr, int ft, float fw, int hs, float4 g0,
+                                       float4 grad, float bgrad, int lane) {
+    const int d4 = d >> 2;
+    const int c = lane;
+    const float gx = grad.x * fw, gy = grad.y * fw, gz = grad.z * fw, gw = grad.w * fw;
     if (hs >= 0) {
-        int* lock = h.locks + hs;
+        int* lock = hlocks + hs;
         if (hot_lock(lock, lane)) {
-            float4* sb = h.acc + (size_t)hs * h.stride;
-#pragma unroll
-            for (int j = 0; j < NCH; j++) {
-                const int c = lane + 32 * j;
-                if (c < d4) {
-                    const float gx = grad[4 * j] * fw, gy = grad[4 * j + 1] * fw, gz = grad[4 * j + 2] * fw,
-                                gw = grad[4 * j + 3] * fw;
-                    float4 aw = sb[c], ag = sb[d4 + c];
-                    aw.x -= lr * rsqrt_ftz(g0[j].x) * gx; aw.y -= lr * rsqrt_ftz(g0[j].y) * gy;
-                    aw.z -= lr * rsqrt_ftz(g0[j].z) * gz; aw.w -= lr * rsqrt_ftz(g0[j].w) * gw;
-                    ag.x = fmaf(gx, gx, ag.x); ag.y = fmaf(gy, gy, ag.y);
-                    ag.z = fmaf(gz, gz, ag.z); ag.w = fmaf(gw, gw, ag.w);
-                    sb[c] = aw;
-                    sb[d4 + c] = ag;
-                }
+            float4* sb = hacc + (size_t)hs * hstride;
+            if (c < d4) {
+                float4 aw = sb[c], ag = sb[d4 + c];
+                aw.x -= lr * rsqrt_ftz(g0.x) * gx; aw.y -= lr * rsqrt_ftz(g0.y) * gy;
+                aw.z -= lr * rsqrt_ftz(g0.z) * gz; aw.w -= lr * rsqrt_ftz(g0.w) * gw;
+                ag.x = fmaf(gx, gx, ag.x); ag.y = fmaf(gy, gy, ag.y);
+                ag.z = fmaf(gz, gz, ag.z); ag.w = fmaf(gw, gw, ag.w);
+                sb[c] = aw;
+                sb[d4 + c] = ag;
             }
             if (lane == 0) {
                 const float g = bgrad * fw;
-                const float bg0 = __ldcg(t.bg + ft);
+                const float bg0 = __ldcg(tbg + ft);
                 float4 ab = sb[2 * d4];
                 ab.x -= lr * rsqrt_ftz(bg0) * g;
                 ab.y = fmaf(g, g, ab.y);
@@ -419,23 +414,16 @@ __device__ __forceinline__ void apply_row(DevTable& t, const HotSmem& h, const D
             return;
         }
     }
-#pragma unroll
-    for (int j = 0; j < NCH; j++) {
-        const int c = lane + 32 * j;
-        if (c < d4) {
-            const float gx = grad[4 * j] * fw, gy = grad[4 * j + 1] * fw, gz = grad[4 * j + 2] * fw,
-                        gw = grad[4 * j + 3] * fw;
-            const size_t o = (size_t)ft * d + c * 4;
-            red_add_v4(t.w + o, -lr * rsqrt_ftz(g0[j].x) * gx, -lr * rsqrt_ftz(g0[j].y) * gy,
-                       -lr * rsqrt_ftz(g0[j].z) * gz, -lr * rsqrt_ftz(g0[j].w) * gw);
-            red_add_v4(t.g + o, gx * gx, gy * gy, gz * gz, gw * gw);
-        }
+    if (c < d4) {
+        const size_t o = (size_t)ft * d + c * 4;
+        red_add_v4(tw + o, -lr * rsqrt_ftz(g0.x) * gx, -lr * rsqrt_ftz(g0.y) * gy, -lr * rsqrt_ftz(g0.z) * gz,
+                   -lr * rsqrt_ftz(g0.w) * gw);
+        if (hs >= 0) red_add_v4(tg + o, gx * gx, gy * gy, gz * gz, gw * gw);  // (direct rows: added by the caller's atomic)
     }
     if (hs >= 0 && lane == 0) {  // slot busy: its bias goes the direct way as well
         const float g = bgrad * fw;
-        const float bg0 = __ldcg(t.bg + ft);
-        red_add(t.b + ft, -lr * rsqrt_ftz(bg0) * g);
-        red_add(t.bg + ft, g * g);
+        const float bg0 = atomicAdd(tbg + ft, g * g);
+        red_add(tb + ft, -lr * rsqrt_ftz(bg0) * g);
     }
 }
 
@@ -445,6 +433,7 @@ template <int KPL>
 __device__ __forceinline__ void scatter_b(const DevCsr& f, DevTable& t, const int32_t* __restrict__ hot_slot,
                                           const HotSmem& h, const DevModel& m, int row, const FeatRow& fr,
                                           const float (&grad)[KPL], float bgrad, int lane) {
+    static_assert(KPL == 4, "the hot-row path holds one float4 chunk per lane (d <= 128)");
     constexpr int NCH = KPL / 4;
     const int d = m.d, d4 = d >> 2;
     const float lr = m.lr;
@@ -464,9 +453,8 @@ __device__ __forceinline__ void scatter_b(const DevCsr& f, DevTable& t, const in
         // biases of the rows without a slot: one feature per lane, all in flight together
         if (lane < cnt && my_hs < 0) {
             const float g = bgrad * my_fw;
-            const float g0 = __ldcg(t.bg + my_ft);
+            const float g0 = atomicAdd(t.bg + my_ft, g * g);
             red_add(t.b + my_ft, -lr * rsqrt_ftz(g0) * g);
-            red_add(t.bg + my_ft, g * g);
         }
 #pragma unroll 1
         for (int i0 = 0; i0 < cnt; i0 += FB) {
@@ -478,8 +466,19 @@ __device__ __forceinline__ void scatter_b(const DevCsr& f, DevTable& t, const in
 #pragma unroll
                 for (int j = 0; j < NCH; j++) {
                     const int c = lane + 32 * j;
-                    g0[k][j] = (i < cnt && c < d4) ? ldcg4(t.g + (size_t)ft * d + c * 4)
-                                                   : make_float4(1.f, 1.f, 1.f, 1.f);
+                    g0[k][j] = make_float4(1.f, 1.f, 1.f, 1.f);
+                    if (i < cnt && c < d4) {
+                        const int hs = __shfl_sync(LFM_FULL, my_hs, i & 31);
+                        float* G = t.g + (size_t)ft * d + c * 4;
+                        if (hs >= 0) {
+                            g0[k][j] = ldcg4(G);     // slot row: the accumulator delta goes to shared memory
+                        } else {                     // direct row: add g^2 now and keep what was there before
+                            const float fw = __shfl_sync(LFM_FULL, my_fw, i & 31);
+                            const float gx = grad[4 * j] * fw, gy = grad[4 * j + 1] * fw, gz = grad[4 * j + 2] * fw,
+                                        gw = grad[4 * j + 3] * fw;
+                            g0[k][j] = atom_add_v4(G, gx * gx, gy * gy, gz * gz, gw * gw);
+                        }
+                    }
                 }
             }
 #pragma unroll
@@ -489,7 +488,8 @@ __device__ __forceinline__ void scatter_b(const DevCsr& f, DevTable& t, const in
                 const int ft = __shfl_sync(LFM_FULL, my_ft, i & 31);
                 const float fw = __shfl_sync(LFM_FULL, my_fw, i & 31);
                 const int hs = __shfl_sync(LFM_FULL, my_hs, i & 31);
-                apply_row<KPL>(t, h, m, ft, fw, hs, g0[k], grad, bgrad, lane);
+                apply_row(t.w, t.g, t.b, t.bg, h.acc, h.locks, h.stride, d, lr, ft, fw, hs, g0[k][0],
+                          make_float4(grad[0], grad[1], grad[2], grad[3]), bgrad, lane);
             }
         }
     }

@@ -337,7 +337,17 @@ __device__ __forceinline__ int slot_probe_index(int lo, int hi, int sub) {
 // requested together and judged in draw order, so the outcome is exactly that of drawing them one
 // at a time (the second one is simply not consumed when the first is taken), while the number of
 // dependent L2 round trips per interaction is halved.
-template <int LOSS, int D, int VPL, int MINB, bool BITMAP = false, int KSR = 1, bool PROBE = false, bool SPEC = false>
+//
+// ATOMG (lfm_set_atomic_accumulators, default on): the accumulator update is an atomic add that
+// RETURNS the old value, and the step is scaled by that value -- lr / sqrt(G) with G containing
+// every earlier update of the element, as in the sequential algorithm.  With a plain
+// read-then-reduce, the ~10^2 interactions in flight that touch the same popular item all scale
+// their step by the same stale G; while accumulators are still small that overshoots, and it
+// costs top-of-ranking precision at C2 shape (tests/test_gpu_tierb.py: p@10 outside the
+// reference's own band without it).  The accumulator rows of the user and the positive item are
+// then no longer staged, which halves the staging traffic.
+template <int LOSS, int D, int VPL, int MINB, bool BITMAP = false, int KSR = 1, bool PROBE = false, bool SPEC = false,
+          bool ATOMG = false>
 __global__ void __launch_bounds__(256, MINB) fast_slot_kernel(FitArgs a, const Tuple* __restrict__ tuples) {
     constexpr bool PAIRWISE = LOSS != LOSS_LOGISTIC;  // has a negative item and a positives CSR
     constexpr bool KOS = LOSS == LOSS_KOS;            // positive item chosen in-kernel (T:975-1011)
@@ -346,7 +356,7 @@ __global__ void __launch_bounds__(256, MINB) fast_slot_kernel(FitArgs a, const T
     typedef TupleScalars<KSR> Scalars;
     constexpr int LPR = D / (4 * VPL);
     constexpr int NS = 32 / LPR;
-    constexpr int BUFF = 4 * D;  // floats per slot per buffer: u, p, Gu, Gp rows
+    constexpr int BUFF = (ATOMG ? 2 : 4) * D;  // floats per slot per buffer: u, p (+ Gu, Gp rows unless ATOMG)
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int sub = lane % LPR, slot = lane / LPR;
@@ -369,10 +379,10 @@ __global__ void __launch_bounds__(256, MINB) fast_slot_kernel(FitArgs a, const T
         for (int v = 0; v < VPL; v++) {
             const int o = (sub + LPR * v) * 4;
             cp_async16(buf + 0 * D + o, m.user.w + (size_t)tp.user * D + o);
-            cp_async16(buf + 2 * D + o, m.user.g + (size_t)tp.user * D + o);
+            if (!ATOMG) cp_async16(buf + 2 * D + o, m.user.g + (size_t)tp.user * D + o);
             if (!KOS) {
                 cp_async16(buf + 1 * D + o, m.item.w + (size_t)tp.item * D + o);
-                cp_async16(buf + 3 * D + o, m.item.g + (size_t)tp.item * D + o);
+                if (!ATOMG) cp_async16(buf + 3 * D + o, m.item.g + (size_t)tp.item * D + o);
             }
         }
         sc.ub = __ldcg(m.user.b + tp.user);
@@ -672,7 +682,58 @@ __global__ void __launch_bounds__(256, MINB) fast_slot_kernel(FitArgs a, const T
 
         // ---- update (T:454-534 / T:537-649): rows + biases of a slot, one instruction stream ----
         const bool upd = (LOSS == LOSS_WARP || KOS) ? neg_id >= 0 : valid;
-        if (__any_sync(LFM_FULL, upd)) {
+        if constexpr (ATOMG) {
+            if (upd) {
+                const size_t op = (size_t)pos_id * D, ou = (size_t)cur.user * D;
+                const size_t on = PAIRWISE ? (size_t)neg_id * D : 0;
+                // biases first: sub 0 positive / item, 1 negative (pairwise) or user (logistic), 2 user
+                float* bp = nullptr;
+                float* bgp = nullptr;
+                float bgrad = 0.0f;
+                if constexpr (PAIRWISE) {
+                    if (sub < 3) {
+                        bp = sub == 0 ? m.item.b + pos_id : sub == 1 ? m.item.b + neg_id : m.user.b + cur.user;
+                        bgp = sub == 0 ? m.item.bg + pos_id : sub == 1 ? m.item.bg + neg_id : m.user.bg + cur.user;
+                        bgrad = sub == 0 ? -loss : loss;
+                    }
+                } else {
+                    if (sub < 2) {
+                        bp = sub == 0 ? m.item.b + cur.item : m.user.b + cur.user;
+                        bgp = sub == 0 ? m.item.bg + cur.item : m.user.bg + cur.user;
+                        bgrad = loss;
+                    }
+                }
+                float bold = 1.0f;
+                if (bp) bold = atomicAdd(bgp, bgrad * bgrad);
+#pragma unroll
+                for (int v = 0; v < VPL; v++) {
+                    const int o = (sub + LPR * v) * 4;
+                    const float4 p4 = KOS ? pk : *(const float4*)(buf + 1 * D + o);
+                    const float lx = loss * u[v].x, ly = loss * u[v].y, lz = loss * u[v].z, lw = loss * u[v].w;
+                    float4 gu;   // gradient of the user row
+                    if constexpr (PAIRWISE)
+                        gu = make_float4(loss * (q[v].x - p4.x), loss * (q[v].y - p4.y), loss * (q[v].z - p4.z),
+                                         loss * (q[v].w - p4.w));
+                    else
+                        gu = make_float4(loss * p4.x, loss * p4.y, loss * p4.z, loss * p4.w);
+                    // accumulate g^2 and get the accumulators as every earlier update left them
+                    const float4 oP = atom_add_v4(m.item.g + op + o, lx * lx, ly * ly, lz * lz, lw * lw);
+                    const float4 oU = atom_add_v4(m.user.g + ou + o, gu.x * gu.x, gu.y * gu.y, gu.z * gu.z, gu.w * gu.w);
+                    float4 oN = make_float4(1.f, 1.f, 1.f, 1.f);
+                    if constexpr (PAIRWISE) oN = atom_add_v4(m.item.g + on + o, lx * lx, ly * ly, lz * lz, lw * lw);
+                    const float sg = PAIRWISE ? -1.0f : 1.0f;  // positive item: -loss * u (pairwise), +loss * u (logistic)
+                    red_add_v4(m.item.w + op + o, -lr * rsqrt_ftz(oP.x) * sg * lx, -lr * rsqrt_ftz(oP.y) * sg * ly,
+                               -lr * rsqrt_ftz(oP.z) * sg * lz, -lr * rsqrt_ftz(oP.w) * sg * lw);
+                    red_add_v4(m.user.w + ou + o, -lr * rsqrt_ftz(oU.x) * gu.x, -lr * rsqrt_ftz(oU.y) * gu.y,
+                               -lr * rsqrt_ftz(oU.z) * gu.z, -lr * rsqrt_ftz(oU.w) * gu.w);
+                    if constexpr (PAIRWISE)
+                        red_add_v4(m.item.w + on + o, -lr * rsqrt_ftz(oN.x) * lx, -lr * rsqrt_ftz(oN.y) * ly,
+                                   -lr * rsqrt_ftz(oN.z) * lz, -lr * rsqrt_ftz(oN.w) * lw);
+                }
+                if (bp) red_add(bp, -lr * rsqrt_ftz(bold) * bgrad);
+                if (sub == 0) c_upd++;
+            }
+        } else if (__any_sync(LFM_FULL, upd)) {
             float4 gn[VPL];
             float4 pk_g = make_float4(1.f, 1.f, 1.f, 1.f);  // k-OS: the chosen positive's accumulator row
             float bgv = 1.0f;  // bias accumulator: sub 0 item (positive), 1 negative / user, 2 user
@@ -773,13 +834,13 @@ FastGrid fast_grid(K kernel, int64_t warps_wanted, int64_t warps_cap) {
     return g;
 }
 
-template <int LOSS, int D, int VPL, int MINB, bool BITMAP, int KSR = 1, bool SPEC = false>
+template <int LOSS, int D, int VPL, int MINB, bool BITMAP, int KSR = 1, bool SPEC = false, bool ATOMG = false>
 cudaError_t launch_slot_impl(const FitArgs& b, const Tuple* tp, int64_t count, cudaStream_t st) {
     constexpr int LPR = D / (4 * VPL);
     constexpr int NS = 32 / LPR;
     constexpr int BT = 256, WPB = BT / 32;  // threads / warps per block
-    const size_t smem = (size_t)WPB * NS * 2 * 4 * D * sizeof(float);
-    auto kern = fast_slot_kernel<LOSS, D, VPL, MINB, BITMAP, KSR, false, SPEC>;
+    const size_t smem = (size_t)WPB * NS * 2 * (ATOMG ? 2 : 4) * D * sizeof(float);
+    auto kern = fast_slot_kernel<LOSS, D, VPL, MINB, BITMAP, KSR, false, SPEC, ATOMG>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BT, smem);
@@ -797,8 +858,16 @@ cudaError_t launch_slot_impl(const FitArgs& b, const Tuple* tp, int64_t count, c
     return cudaGetLastError();
 }
 
+static std::atomic<int> g_atomg{1};
+
 template <int LOSS, int D, int VPL, int MINB, int KSR = 1, bool SPEC = false>
 cudaError_t launch_slot(const FitArgs& b, const Tuple* tp, int64_t count, cudaStream_t st) {
+    if (g_atomg.load()) {
+        if constexpr (LOSS != LOSS_LOGISTIC) {
+            if (b.pos_bitmap) return launch_slot_impl<LOSS, D, VPL, MINB, true, KSR, SPEC, true>(b, tp, count, st);
+        }
+        return launch_slot_impl<LOSS, D, VPL, MINB, false, KSR, SPEC, true>(b, tp, count, st);
+    }
     if constexpr (LOSS != LOSS_LOGISTIC) {
         if (b.pos_bitmap) return launch_slot_impl<LOSS, D, VPL, MINB, true, KSR, SPEC>(b, tp, count, st);
     }
@@ -901,6 +970,7 @@ extern "C" int lfm_set_tuning(int variant) {
 }
 
 extern "C" int lfm_set_probe(int enabled) { return g_probe.exchange(enabled ? 1 : 0); }
+extern "C" int lfm_set_atomic_accumulators(int enabled) { return g_atomg.exchange(enabled ? 1 : 0); }
 
 // Set by lfm_set_fast_path (tests use it to exercise the generic kernels on fast-eligible inputs).
 static std::atomic<int> g_fast_enabled{1};

@@ -125,74 +125,98 @@ __device__ __forceinline__ void build_user_tile(const DevCsr& usf, const DevMode
     else for (int j = lane; j <= d; j += 32) ut[j * RANK_UT + w] = 0.0f;
 }
 
-__global__ void __launch_bounds__(RANK_UT * 32) predict_ranks_tiled_kernel(
+// RANK_G user tiles run side by side in one CTA (one group of RANK_UT warps each) and walk the
+// item table in lockstep (a barrier per 1024-item step): the second and third group find the item
+// values the first one pulled from L2 in the SM's L1, which cuts the L2 -> SM traffic per score by
+// RANK_G (at 8 users per item value the stream was L2-bandwidth-bound: profiles/README.md).
+#define RANK_G 3
+#define RANK_GT (RANK_UT * 32)  // threads per group
+
+__global__ void __launch_bounds__(RANK_G * RANK_GT, 1) predict_ranks_tiled_kernel(
     DevCsr usf, DevCsr test, DevCsr train, DevModel m, const float* __restrict__ irt, int ld,
     const int32_t* __restrict__ active, const int32_t* __restrict__ n_active_p, float* ranks) {
-    extern __shared__ __align__(16) float sm[];
+    extern __shared__ __align__(16) float sm_all[];
     const int d = m.d, n_items = test.cols;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int g = threadIdx.x / RANK_GT, tl = threadIdx.x % RANK_GT;  // group, thread within the group
+    const int lane = tl & 31, w = tl >> 5;
+    const int per_group = RANK_UT * (d + 1) + RANK_UT * RANK_TCH * 3 + RANK_UT * RANK_UT * RANK_TCH;  // 4-byte words
+    float* sm = sm_all + (size_t)g * ((per_group + 3) & ~3);
     float* ut = sm;                                        // [d+1][UT] transposed user tile
     float* tp = ut + RANK_UT * (d + 1);                    // [UT][TCH] test scores
     int* tid = (int*)(tp + RANK_UT * RANK_TCH);            // [UT][TCH] test item ids
     int* cnt = tid + RANK_UT * RANK_TCH;                   // [UT warps][UT][TCH] partial counts
     int* sub = cnt + RANK_UT * RANK_UT * RANK_TCH;         // [UT][TCH] train-positive counts
-    __shared__ int s_user[RANK_UT], s_ts[RANK_UT], s_T[RANK_UT];
+    __shared__ int s_user[RANK_G][RANK_UT], s_ts[RANK_G][RANK_UT], s_T[RANK_G][RANK_UT], s_maxT[RANK_G];
     const int n_active = *n_active_p;
 
-    for (int tile = blockIdx.x; tile * RANK_UT < n_active; tile += gridDim.x) {
+    for (int tile0 = blockIdx.x * RANK_G; tile0 * RANK_UT < n_active; tile0 += gridDim.x * RANK_G) {
+        const int tile = tile0 + g;
         __syncthreads();
-        if (threadIdx.x < RANK_UT) {
-            int k = tile * RANK_UT + threadIdx.x;
+        if (tl < RANK_UT) {
+            int k = tile * RANK_UT + tl;
             int u = k < n_active ? active[k] : -1;
-            s_user[threadIdx.x] = u;
-            s_ts[threadIdx.x] = u >= 0 ? test.indptr[u] : 0;
-            s_T[threadIdx.x] = u >= 0 ? test.indptr[u + 1] - test.indptr[u] : 0;
+            s_user[g][tl] = u;
+            s_ts[g][tl] = u >= 0 ? test.indptr[u] : 0;
+            s_T[g][tl] = u >= 0 ? test.indptr[u + 1] - test.indptr[u] : 0;
         }
         __syncthreads();
-        build_user_tile(usf, m, s_user, ut, w, lane);
-        int maxT = 0;
-        for (int u = 0; u < RANK_UT; u++) maxT = max(maxT, s_T[u]);
+        build_user_tile(usf, m, s_user[g], ut, w, lane);
+        if (tl == 0) {
+            int mt = 0;
+            for (int u = 0; u < RANK_UT; u++) mt = max(mt, s_T[g][u]);
+            s_maxT[g] = mt;
+        }
         __syncthreads();
+        int maxT = 0;  // block-uniform: every group walks the same number of test chunks
+        for (int gg = 0; gg < RANK_G; gg++) maxT = max(maxT, s_maxT[gg]);
 
         for (int c0 = 0; c0 < maxT; c0 += RANK_TCH) {
             // B0: this chunk's test scores (T:1283-1298) and cleared counters
-            for (int x = threadIdx.x; x < RANK_UT * RANK_TCH; x += blockDim.x) {
+            for (int x = tl; x < RANK_UT * RANK_TCH; x += RANK_GT) {
                 int u = x / RANK_TCH, t = x % RANK_TCH;
-                if (c0 + t < s_T[u]) {
-                    int id = test.indices[s_ts[u] + c0 + t];
+                if (c0 + t < s_T[g][u]) {
+                    int id = test.indices[s_ts[g][u] + c0 + t];
                     tid[x] = id;
                     tp[x] = rank_score(ut, u, irt, ld, d, id);
                 }
                 sub[x] = 0;
             }
-            for (int x = threadIdx.x; x < RANK_UT * RANK_UT * RANK_TCH; x += blockDim.x) cnt[x] = 0;
+            for (int x = tl; x < RANK_UT * RANK_UT * RANK_TCH; x += RANK_GT) cnt[x] = 0;
             __syncthreads();
 
             // B + C: stream the catalogue once.  The test item itself is part of the stream: its
             // score there is the very same sequence of operations as tp[], so it counts itself
             // exactly once unless the score is NaN; that 1 is taken off in E instead of testing
             // `item != test item` on every comparison (T:1305-1306).
-            for (int i0 = 0; i0 < n_items; i0 += blockDim.x * RANK_IT) {
-                const int i = i0 + threadIdx.x * RANK_IT;
+            for (int i0 = 0; i0 < n_items; i0 += RANK_GT * RANK_IT) {
+                const int i = i0 + tl * RANK_IT;
                 float acc[RANK_IT][RANK_UT];
                 if (i < ld) tile_scores(ut, irt, ld, d, i, acc);
+                const float ninf = __int_as_float(0xff800000);
+#pragma unroll
+                for (int k = 0; k < RANK_IT; k++)
+                    if (i + k >= n_items) {
+#pragma unroll
+                        for (int u = 0; u < RANK_UT; u++) acc[k][u] = ninf;  // past the catalogue: never >= anything
+                    }
 #pragma unroll
                 for (int u = 0; u < RANK_UT; u++) {
-                    const int Tc = min(RANK_TCH, s_T[u] - c0);
+                    const int Tc = min(RANK_TCH, s_T[g][u] - c0);
                     for (int t = 0; t < Tc; t++) {
                         const float ref = tp[u * RANK_TCH + t];
                         int c = 0;
 #pragma unroll
-                        for (int k = 0; k < RANK_IT; k++) c += (i + k < n_items && acc[k][u] >= ref) ? 1 : 0;
+                        for (int k = 0; k < RANK_IT; k++) c += (acc[k][u] >= ref) ? 1 : 0;
                         c = __reduce_add_sync(LFM_FULL, c);
                         if (lane == 0) cnt[(w * RANK_UT + u) * RANK_TCH + t] += c;
                     }
                 }
+                __syncthreads();  // keep the groups on the same 1024-item step (shared L1 lines)
             }
             // D: the train positives' share of those counts (warp w <-> user w)
             {
-                const int u = s_user[w];
-                const int Tc = min(RANK_TCH, s_T[w] - c0);
+                const int u = s_user[g][w];
+                const int Tc = min(RANK_TCH, s_T[g][w] - c0);
                 if (u >= 0 && Tc > 0 && u < train.rows) {
                     const int rs = train.indptr[u], re = train.indptr[u + 1];
                     for (int e0 = rs; e0 < re; e0 += 32) {
@@ -212,14 +236,14 @@ __global__ void __launch_bounds__(RANK_UT * 32) predict_ranks_tiled_kernel(
             }
             __syncthreads();
             // E: reduce over warps and accumulate into ranks (pre-zeroed by the caller, L:968-975)
-            for (int x = threadIdx.x; x < RANK_UT * RANK_TCH; x += blockDim.x) {
+            for (int x = tl; x < RANK_UT * RANK_TCH; x += RANK_GT) {
                 int u = x / RANK_TCH, t = x % RANK_TCH;
-                if (c0 + t < s_T[u]) {
+                if (c0 + t < s_T[g][u]) {
                     int total = 0;
                     for (int ww = 0; ww < RANK_UT; ww++) total += cnt[(ww * RANK_UT + u) * RANK_TCH + t];
                     const float ref = tp[x];
                     if (ref == ref) total -= 1;  // the test item's own (non-NaN) score in the stream
-                    ranks[s_ts[u] + c0 + t] += (float)(total - sub[x]);
+                    ranks[s_ts[g][u] + c0 + t] += (float)(total - sub[x]);
                 }
             }
             __syncthreads();
@@ -547,13 +571,13 @@ cudaError_t lfm_launch_predict_ranks(const DevCsr& itf, const DevCsr& usf, const
     cudaError_t e = cudaMemsetAsync(count, 0, sizeof(int32_t), st);
     if (e != cudaSuccess) return e;
     compact_users_kernel<<<(test.rows + 255) / 256, 256, 0, st>>>(test, active, count);
-    size_t smem = sizeof(float) * (RANK_UT * (m.d + 1) + RANK_UT * RANK_TCH) +
-                  sizeof(int) * (RANK_UT * RANK_TCH + RANK_UT * RANK_UT * RANK_TCH + RANK_UT * RANK_TCH);
+    const size_t per_group = (size_t)RANK_UT * (m.d + 1) + RANK_UT * RANK_TCH * 3 + RANK_UT * RANK_UT * RANK_TCH;
+    size_t smem = sizeof(float) * RANK_G * ((per_group + 3) & ~(size_t)3);
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(predict_ranks_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int grid = (test.rows + RANK_UT - 1) / RANK_UT;
-    if (grid > 148 * 4) grid = 148 * 4;
-    predict_ranks_tiled_kernel<<<grid, RANK_UT * 32, smem, st>>>(usf, test, train, m, repr_t, ld, active, count, ranks);
+    int grid = (test.rows + RANK_UT * RANK_G - 1) / (RANK_UT * RANK_G);
+    if (grid > 148) grid = 148;  // one persistent CTA (three user tiles) per SM
+    predict_ranks_tiled_kernel<<<grid, RANK_G * RANK_GT, smem, st>>>(usf, test, train, m, repr_t, ld, active, count, ranks);
     if (launches) *launches += 3;
     return cudaGetLastError();
 }

@@ -196,7 +196,7 @@ def test_midscale_hogwild_matches_oracle_heldout_metrics():
     assert abs(res[0][0] - res[1][0]) <= 0.12 * res[0][0] + 0.005, res
 
 
-@pytest.mark.parametrize("variant", (0, 4, 5, 6, 7, 8))
+@pytest.mark.parametrize("variant", (0, 4, 5, 6, 7, 8, 9, 10))
 @pytest.mark.parametrize("bitmap", (True, False))
 def test_every_warp_kernel_variant_trains(variant, bitmap):
     """lfm_set_tuning selects the WARP fast-path kernel; every variant (with and without the

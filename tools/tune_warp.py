@@ -12,6 +12,8 @@ variants = [int(v) for v in (sys.argv[1].split(",") if len(sys.argv) > 1 else "0
 nnz = int(sys.argv[2]) if len(sys.argv) > 2 else B.NNZ
 prob = B.Problem(B.N_USERS, B.N_ITEMS, nnz, B.D, seed=2, device="cuda")
 itf, usf, pos = fast.CSRMatrix(prob.itf), fast.CSRMatrix(prob.usf), fast.CSRMatrix(prob.pos)
+atomg = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+fast.set_atomic_accumulators(atomg)
 for v in variants:
     fast.set_tuning(v)
     holder = prob.holder(fast)
@@ -22,6 +24,6 @@ for v in variants:
     plan.close()
     ms = sum(c["train_kernel_ms"] for c in cs) / len(cs)
     ab = sum(B.algorithmic_bytes(c, B.D) for c in cs) / len(cs)
-    print(json.dumps({"variant": v, "train_ms": round(ms, 3), "M_inter_per_s": round(cs[0]["positives"] / ms / 1e3, 1),
+    print(json.dumps({"variant": v, "atomic_accumulators": atomg, "train_ms": round(ms, 3), "M_inter_per_s": round(cs[0]["positives"] / ms / 1e3, 1),
                       "alg_GBps": round(ab / ms / 1e6, 1), "S": round(cs[-1]["negatives_drawn"] / cs[-1]["positives"], 3),
                       "U": round(cs[-1]["updates"] / cs[-1]["positives"], 3)}), flush=True)

@@ -133,7 +133,8 @@ int lfm_unpin_host(void *ptr);
 
 /* ---- tuning / test knobs (process-wide; each returns the previous value) ------------ */
 /* WARP slot-kernel variant: 0 first-generation warp-per-interaction kernel; 4/5 one float4 per
- * lane at 3/4 CTAs per SM; 6/7/8 two float4 per lane at 2/3/4 CTAs per SM (default 7). */
+ * lane at 3/4 CTAs per SM; 6/7/8 two float4 per lane at 2/3/4 CTAs per SM; 9/10 = 7/6 with two
+ * candidates per slot per round (default 9). */
 int lfm_set_tuning(int variant);
 /* 0: route fast-path-eligible problems through the generic kernels (tests). */
 int lfm_set_fast_path(int enabled);
@@ -148,6 +149,9 @@ int lfm_set_replay_fast(int enabled);
  * the old value and the step is scaled by it (every earlier update of the element is seen, whatever
  * is in flight); 0 = read-then-reduce (round-1 behaviour). */
 int lfm_set_atomic_accumulators(int enabled);
+/* predict_ranks tiling: 1 = one 8-user tile per CTA; 3 = three tiles per CTA in lockstep over the
+ * item table (L1 sharing).  Returns the previous value. */
+int lfm_set_rank_groups(int groups);
 /* 1: run the slot kernels as ONE warp with ONE interaction in flight and the reference's rand_r
  * negatives, so that only their arithmetic differs from the oracle (tests/test_gpu_probe.py). */
 int lfm_set_probe(int enabled);

@@ -124,6 +124,7 @@ LIB_ONLY = {
     "lfm_set_fast_path": (C.c_int, [C.c_int]),
     "lfm_set_inflight_divisor": (C.c_int, [C.c_int]),
     "lfm_set_probe": (C.c_int, [C.c_int]),
+    "lfm_set_rank_groups": (C.c_int, [C.c_int]),
     "lfm_set_atomic_accumulators": (C.c_int, [C.c_int]),
     "lfm_set_replay_fast": (C.c_int, [C.c_int]),
     "lfm_set_hot_rows": (C.c_int, [C.c_int]),

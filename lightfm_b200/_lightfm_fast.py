@@ -92,6 +92,11 @@ def set_atomic_accumulators(enabled):
     return _lib.lfm_set_atomic_accumulators(int(bool(enabled)))
 
 
+def set_rank_groups(groups):
+    """predict_ranks tiling: 1 or 3 user tiles per CTA (see lfm_set_rank_groups)."""
+    return _lib.lfm_set_rank_groups(int(groups))
+
+
 def set_replay_fast(enabled):
     """Replay mode: use the prefetching WARP kernel where it applies (default on; both bit-equal)."""
     return _lib.lfm_set_replay_fast(int(bool(enabled)))

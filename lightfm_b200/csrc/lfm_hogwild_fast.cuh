@@ -879,8 +879,8 @@ static std::atomic<int> g_probe{0};
 template <int LOSS, int D, int VPL, int MINB>
 cudaError_t launch_probe(const FitArgs& b, const Tuple* tp, cudaStream_t st) {
     constexpr int NS = 32 / (D / (4 * VPL));
-    const size_t smem = (size_t)NS * 2 * 4 * D * sizeof(float);
-    auto kern = fast_slot_kernel<LOSS, D, VPL, MINB, false, 1, true>;
+    const size_t smem = (size_t)NS * 2 * 2 * D * sizeof(float);
+    auto kern = fast_slot_kernel<LOSS, D, VPL, MINB, false, 1, true, false, true>;  // PROBE, ATOMG
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<1, 32, smem, st>>>(b, tp);
     return cudaGetLastError();
@@ -890,12 +890,13 @@ cudaError_t launch_probe(const FitArgs& b, const Tuple* tp, cudaStream_t st) {
 //   0      fast_rank_kernel for WARP as well (warp per interaction, speculative negatives)
 //   4 / 5  fast_slot_kernel, one float4 per lane, 3 / 4 CTAs per SM
 //   6/7/8  fast_slot_kernel, two float4 per lane (twice the interactions per warp; d >= 32),
-//          2 / 3 / 4 CTAs per SM                                   [7 = default, fastest on C2]
+//          2 / 3 / 4 CTAs per SM
 //   9/10   as 7 / 6 with two speculative candidates per slot per round (SPEC)
+//          [9 = default: 9.84 ms vs 10.65 ms for 7 on C2 with atomic accumulators]
 // Also tried and dropped (within +-1.5 % of variant 7 once the bitmap was in): 128-thread blocks
 // at 6-8 CTAs per SM (up to 28 warps / SM), and L2 evict-first cache hints on the tuple stream
 // and the CSR probes.
-static std::atomic<int> g_tuning{7};
+static std::atomic<int> g_tuning{9};
 
 template <int LOSS, int LPR>
 cudaError_t launch_fast(const FitArgs& a, const Tuple* tuples, int64_t begin, int64_t count,

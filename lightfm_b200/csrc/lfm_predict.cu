@@ -8,6 +8,8 @@
 //
 // Reference: predict_lightfm T:1185-1229, predict_ranks T:1232-1323,
 // calculate_auc_from_rank T:1326-1376, __test_in_positives T:1380-1385.
+#include <atomic>
+
 #include "lfm_common.cuh"
 
 namespace {
@@ -129,9 +131,9 @@ __device__ __forceinline__ void build_user_tile(const DevCsr& usf, const DevMode
 // item table in lockstep (a barrier per 1024-item step): the second and third group find the item
 // values the first one pulled from L2 in the SM's L1, which cuts the L2 -> SM traffic per score by
 // RANK_G (at 8 users per item value the stream was L2-bandwidth-bound: profiles/README.md).
-#define RANK_G 3
 #define RANK_GT (RANK_UT * 32)  // threads per group
 
+template <int RANK_G>
 __global__ void __launch_bounds__(RANK_G * RANK_GT, 1) predict_ranks_tiled_kernel(
     DevCsr usf, DevCsr test, DevCsr train, DevModel m, const float* __restrict__ irt, int ld,
     const int32_t* __restrict__ active, const int32_t* __restrict__ n_active_p, float* ranks) {
@@ -555,6 +557,14 @@ cudaError_t lfm_launch_predict(const DevCsr& itf, const DevCsr& usf, const DevMo
 }
 
 
+// 1: one user tile per CTA (3 CTAs per SM); 3: three tiles per CTA walking the item table in lockstep
+static std::atomic<int> g_rank_groups{1};
+extern "C" int lfm_set_rank_groups(int groups) {
+    int old = g_rank_groups.load();
+    if (groups == 1 || groups == 3) g_rank_groups.store(groups);
+    return old;
+}
+
 cudaError_t lfm_launch_predict_ranks(const DevCsr& itf, const DevCsr& usf, const DevCsr& test,
                                      const DevCsr& train, const DevModel& m, float* ranks,
                                      float* scratch, cudaStream_t st, int* launches) {
@@ -572,12 +582,21 @@ cudaError_t lfm_launch_predict_ranks(const DevCsr& itf, const DevCsr& usf, const
     if (e != cudaSuccess) return e;
     compact_users_kernel<<<(test.rows + 255) / 256, 256, 0, st>>>(test, active, count);
     const size_t per_group = (size_t)RANK_UT * (m.d + 1) + RANK_UT * RANK_TCH * 3 + RANK_UT * RANK_UT * RANK_TCH;
-    size_t smem = sizeof(float) * RANK_G * ((per_group + 3) & ~(size_t)3);
-    if (smem > 48 * 1024)
-        cudaFuncSetAttribute(predict_ranks_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int grid = (test.rows + RANK_UT * RANK_G - 1) / (RANK_UT * RANK_G);
-    if (grid > 148) grid = 148;  // one persistent CTA (three user tiles) per SM
-    predict_ranks_tiled_kernel<<<grid, RANK_G * RANK_GT, smem, st>>>(usf, test, train, m, repr_t, ld, active, count, ranks);
+    const size_t group_bytes = sizeof(float) * ((per_group + 3) & ~(size_t)3);
+    if (g_rank_groups.load() == 3) {
+        const size_t smem = 3 * group_bytes;
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(predict_ranks_tiled_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int grid = (test.rows + RANK_UT * 3 - 1) / (RANK_UT * 3);
+        if (grid > 148) grid = 148;  // one persistent CTA (three user tiles) per SM
+        predict_ranks_tiled_kernel<3><<<grid, 3 * RANK_GT, smem, st>>>(usf, test, train, m, repr_t, ld, active, count, ranks);
+    } else {
+        if (group_bytes > 48 * 1024)
+            cudaFuncSetAttribute(predict_ranks_tiled_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)group_bytes);
+        int grid = (test.rows + RANK_UT - 1) / RANK_UT;
+        if (grid > 148 * 3) grid = 148 * 3;
+        predict_ranks_tiled_kernel<1><<<grid, RANK_GT, group_bytes, st>>>(usf, test, train, m, repr_t, ld, active, count, ranks);
+    }
     if (launches) *launches += 3;
     return cudaGetLastError();
 }

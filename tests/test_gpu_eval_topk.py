@@ -156,3 +156,39 @@ def test_predict_ranks_register_tiled_kernel_odd_shapes():
                           api.CSRMatrix(train), ranks, H.holder(api, arr, hp), 1)
         outs.append(ranks)
     assert np.array_equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("groups", (1, 3))
+def test_predict_ranks_dense_test_rows_both_tilings(groups):
+    """The reference's tests/test_api.py::test_predict_ranks scenario (every item of every user is a
+    test interaction: 100 > 64 test entries per user, i.e. two chunks per tile), repeated over seeds
+    and a larger catalogue, for both CTA layouts of the rank kernel: bit-equal to the oracle."""
+    cu, orc = H.cuda_native(), H.oracle_native()
+    old = cu.module.set_rank_groups(groups)
+    try:
+        for seed, (n_users, n_items, d) in enumerate([(10, 100, 10)] * 6 + [(53, 1500, 10), (40, 3000, 32)]):
+            rs = np.random.RandomState(seed)
+            arr = H.init_arrays(rs, n_items, n_users, d)
+            arr["item_embeddings"][:] = rs.normal(size=(n_items, d)).astype(np.float32)
+            arr["user_embeddings"][:] = rs.normal(size=(n_users, d)).astype(np.float32)
+            arr["item_biases"][:] = rs.normal(size=n_items).astype(np.float32)
+            test = sp.csr_matrix(np.ones((n_users, min(n_items, 150)), np.float32))
+            test.resize((n_users, n_items))
+            test = sp.csr_matrix(test)
+            train = sp.rand(n_users, n_items, density=0.02, format="csr", random_state=42 + seed).astype(np.float32)
+            train = train - train.multiply(test)
+            train.eliminate_zeros()
+            train = sp.csr_matrix(train, dtype=np.float32)
+            train.sort_indices()
+            hp = H.Hyper(d=d)
+            ii = sp.identity(n_items, dtype=np.float32, format="csr")
+            iu = sp.identity(n_users, dtype=np.float32, format="csr")
+            outs = []
+            for api in (orc, cu):
+                ranks = np.zeros(test.nnz, np.float32)
+                api.predict_ranks(api.CSRMatrix(ii), api.CSRMatrix(iu), api.CSRMatrix(test), api.CSRMatrix(train),
+                                  ranks, H.holder(api, arr, hp), 2)
+                outs.append(ranks)
+            assert np.array_equal(outs[0], outs[1]), (groups, seed, int((outs[0] != outs[1]).sum()))
+    finally:
+        cu.module.set_rank_groups(old)

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 
 # measured on the B200: max relative deviation of any weight after the
 # run stays below these
-BOUNDS = {"warp": 5e-4, "bpr": 5e-4, "logistic": 5e-4}
+BOUNDS = {"warp": 1e-5, "bpr": 1e-5, "logistic": 1e-5}   # measured: 5.7e-7 / 3.7e-7 / 3.5e-7
 
 
 def _fit(api, loss, inter, d, epochs):

@@ -29,12 +29,17 @@ for m in (test, train):
 itf = sp.identity(n_items, dtype=np.float32, format="csr")
 usf = sp.identity(n_users, dtype=np.float32, format="csr")
 ci, cu, ct, ctr = fast.CSRMatrix(itf), fast.CSRMatrix(usf), fast.CSRMatrix(test), fast.CSRMatrix(train)
+groups = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+fast.set_rank_groups(groups)
 for rep in range(2):
     ranks = np.zeros_like(test.data)
     t0 = time.perf_counter()
     fast.predict_ranks(ci, cu, ct, ctr, ranks, holder, 8)
     dt = time.perf_counter() - t0
 scores = slice_users * n_items
-print(json.dumps({"users": slice_users, "items": n_items, "d": d, "test_nnz": int(test.nnz), "wall_s": round(dt, 3),
+kms = fast.last_scoring_ms()
+print(json.dumps({"users": slice_users, "groups_per_cta": groups, "kernel_ms": round(kms, 3),
+                  "G_scores_per_s_kernel": round(scores / kms / 1e6, 1),
+                  "TFLOPs_kernel": round(scores * (2 * d + 1) / kms / 1e9, 2), "items": n_items, "d": d, "test_nnz": int(test.nnz), "wall_s": round(dt, 3),
                   "G_user_item_scores_per_s": round(scores / dt / 1e9, 2),
                   "full_C5_estimate_s": round(dt * n_users / slice_users, 1), "rank_mean": float(ranks.mean())}))

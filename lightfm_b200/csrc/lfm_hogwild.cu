@@ -310,8 +310,10 @@ struct FeatRow {
 
 // Gather in the float4 layout with the row loads of up to FB features in flight at a time
 // (the generic gather walks the features one dependent round trip after the other).
+// (gather_b / scatter_b are deliberately NOT inlined: with three call sites each the kernel was 7 300
+//  instructions and instruction-fetch stalls were its top stall reason, profiles/r2_ncu_c3_hot_v3_summary.txt)
 template <int KPL>
-__device__ __forceinline__ void gather_b(const DevCsr& f, const DevTable& t, const int32_t* __restrict__ hot_slot,
+__device__ __noinline__ void gather_b(const DevCsr& f, const DevTable& t, const int32_t* __restrict__ hot_slot,
                                          int d, int row, Repr<KPL>& r, FeatRow& fr, int lane) {
     constexpr int NCH = KPL / 4;
 #pragma unroll
@@ -377,6 +379,75 @@ __device__ __forceinline__ void gather_b(const DevCsr& f, const DevTable& t, con
     r.b = lfm_warp_sum(bsum);
 }
 
+
+// ---- feature path, WARP: the negative candidates' feature lists are fetched ahead -------------
+// The Philox draws of an interaction are known up front, so the item ids of the next candidates
+// are known before the current one is scored.  A candidate costs three dependent loads
+// (indptr pair -> indices/data -> embedding rows); stages one and two of the NEXT candidates run
+// under the row fetch and scoring of the current one: the row bounds wait in registers, the
+// (feature id, weight) lists stream into a per-warp shared-memory ring with cp.async.
+#define FR_RING 3
+__device__ __forceinline__ void fr_cp_async4(void* smem, const void* gmem) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void fr_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void fr_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void fr_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// stage two: stream the (feature id, weight) list of a row into ring slot `slot` (rows of <= 32 features)
+__device__ __forceinline__ void fr_stage_list(const DevCsr& f, int start, int cnt, int2* ring, int slot, int lane) {
+    if (cnt >= 0 && lane < cnt) {
+        fr_cp_async4(&ring[slot * 32 + lane].x, f.indices + start + lane);
+        fr_cp_async4(&ring[slot * 32 + lane].y, f.data + start + lane);
+    }
+    fr_commit();
+}
+
+// stage three: the rows of a staged list (the lane's entry of the list is read back from the ring)
+template <int KPL>
+__device__ __noinline__ void gather_staged(const DevTable& t, const int32_t* __restrict__ hot_slot, int d, int cnt,
+                                           const int2* ring, int slot, Repr<KPL>& r, FeatRow& fr, int lane) {
+    constexpr int NCH = KPL / 4;
+#pragma unroll
+    for (int k = 0; k < KPL; k++) r.v[k] = 0.0f;
+    const int d4 = d >> 2;
+    const int2 e = ring[slot * 32 + lane];
+    const int my_ft = lane < cnt ? e.x : 0;
+    const float my_fw = lane < cnt ? __int_as_float(e.y) : 0.0f;
+    fr.ft = my_ft; fr.fw = my_fw; fr.cnt = cnt;
+    fr.hs = (hot_slot != nullptr && lane < cnt) ? __ldg(hot_slot + my_ft) : -1;
+    float bsum = lane < cnt ? my_fw * __ldcg(t.b + my_ft) : 0.0f;
+#pragma unroll 1
+    for (int i0 = 0; i0 < cnt; i0 += FB) {
+        float4 x[FB][NCH];
+        float w[FB];
+#pragma unroll
+        for (int k = 0; k < FB; k++) {
+            const int i = i0 + k;
+            const int ft = __shfl_sync(LFM_FULL, my_ft, i & 31);
+            w[k] = __shfl_sync(LFM_FULL, my_fw, i & 31);
+            if (i >= cnt) w[k] = 0.0f;
+#pragma unroll
+            for (int j = 0; j < NCH; j++) {
+                const int c = lane + 32 * j;
+                x[k][j] = (i < cnt && c < d4) ? ldcg4(t.w + (size_t)ft * d + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < FB; k++) {
+#pragma unroll
+            for (int j = 0; j < NCH; j++) {
+                r.v[4 * j] = fmaf(w[k], x[k][j].x, r.v[4 * j]);
+                r.v[4 * j + 1] = fmaf(w[k], x[k][j].y, r.v[4 * j + 1]);
+                r.v[4 * j + 2] = fmaf(w[k], x[k][j].z, r.v[4 * j + 2]);
+                r.v[4 * j + 3] = fmaf(w[k], x[k][j].w, r.v[4 * j + 3]);
+            }
+        }
+    }
+    r.b = lfm_warp_sum(bsum);
+}
+
 // One feature row's share of an Adagrad update (alpha == 0), accumulator chunk already in g0.
 // Hot rows go to the CTA's shared-memory accumulator under the slot lock, everything else (and
 // a hot row whose lock is busy) straight to L2.  One float4 chunk per lane (d <= 128); arguments
@@ -430,7 +501,7 @@ __device__ __noinline__ void apply_row(float* tw, float* tg, float* tb, float* t
 // Adagrad scatter (alpha == 0) in the float4 layout: the accumulator rows of up to FB features
 // are fetched together; `fr` (from the gather of the same row) saves the index loads.
 template <int KPL>
-__device__ __forceinline__ void scatter_b(const DevCsr& f, DevTable& t, const int32_t* __restrict__ hot_slot,
+__device__ __noinline__ void scatter_b(const DevCsr& f, DevTable& t, const int32_t* __restrict__ hot_slot,
                                           const HotSmem& h, const DevModel& m, int row, const FeatRow& fr,
                                           const float (&grad)[KPL], float bgrad, int lane) {
     static_assert(KPL == 4, "the hot-row path holds one float4 chunk per lane (d <= 128)");
@@ -512,11 +583,17 @@ __global__ void __launch_bounds__(HOT ? 512 : 256) hogwild_kernel(FitArgs a, con
         hsm.acc = (float4*)hot_raw;
         hsm.locks = (int*)(hsm.acc + (size_t)a.n_hot * hsm.stride);
         const int words = a.n_hot * hsm.stride * 4 + a.n_hot;
+        // (the per-warp candidate rings follow, 8 B aligned: see fr_ring below)
         for (int i = threadIdx.x; i < words; i += blockDim.x) ((int*)hot_raw)[i] = 0;
         __syncthreads();
     }
     int flush_iter = 0;
     const int lane = threadIdx.x & 31;
+    int2* fr_ring = nullptr;  // [FR_RING][32] (feature id, weight bits) per warp: staged candidate lists
+    if constexpr (HOT) {
+        const size_t off = ((size_t)a.n_hot * (hsm.stride * 16 + 4) + 15) & ~(size_t)15;
+        fr_ring = (int2*)(hot_raw + off) + (size_t)(threadIdx.x >> 5) * FR_RING * 32;
+    }
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     DevModel& m = a.model;
@@ -626,6 +703,9 @@ __global__ void __launch_bounds__(HOT ? 512 : 256) hogwild_kernel(FitArgs a, con
                 pp = __shfl_sync(LFM_FULL, my_val, src);
                 GATHER(a.itf, m.item, a.hot_slot_item, pos_id, item_scale, p, fr_p);
                 c_pos++;
+            } else if constexpr (HOT && LOSS == LOSS_WARP) {
+                // positive item handled together with the first candidates below
+                c_pos++;
             } else {
                 GATHER(a.itf, m.item, a.hot_slot_item, pos_id, item_scale, p, fr_p);
                 pp = dot<KPL>(u, p);
@@ -634,7 +714,67 @@ __global__ void __launch_bounds__(HOT ? 512 : 256) hogwild_kernel(FitArgs a, con
 
             int neg_id = -1;
             float loss = 0.0f;
-            if (LOSS == LOSS_BPR) {
+            if constexpr (HOT && LOSS == LOSS_WARP) {
+                // ---- rank sampling with the candidates' feature lists fetched ahead ----
+                const DevCsr& f = a.itf;
+                auto bounds = [&](int item, int& st, int& cn) {  // stage one (identity: nothing to fetch)
+                    if (f.identity) { st = item; cn = 1; return; }
+                    st = __ldg(f.indptr + item);
+                    cn = __ldg(f.indptr + item + 1) - st;
+                    if (cn > 32) cn = -1;  // long rows take the unstaged gather
+                };
+                auto stage_list = [&](int item, int st, int cn, int slot) {
+                    if (f.identity) {
+                        if (lane == 0) fr_ring[slot * 32] = make_int2(item, __float_as_int(1.0f));
+                        fr_commit();
+                    } else {
+                        fr_stage_list(f, st, cn, fr_ring, slot, lane);
+                    }
+                };
+                int c0 = lfm_bounded(next_u32(), (uint32_t)n_items), c1 = lfm_bounded(next_u32(), (uint32_t)n_items);
+                int ps_st, ps_cn, c0_st, c0_cn, c1_st, c1_cn;
+                bounds(pos_id, ps_st, ps_cn);
+                bounds(c0, c0_st, c0_cn);
+                bounds(c1, c1_st, c1_cn);
+                __syncwarp();
+                stage_list(pos_id, ps_st, ps_cn, 2);   // the positive borrows slot 2 (free until candidate 2 is staged)
+                stage_list(c0, c0_st, c0_cn, 0);
+                fr_wait1();
+                __syncwarp();
+                if (ps_cn >= 0) gather_staged<KPL>(m.item, a.hot_slot_item, d, ps_cn, fr_ring, 2, p, fr_p, lane);
+                else gather_b<KPL>(a.itf, m.item, a.hot_slot_item, d, pos_id, p, fr_p, lane);
+                pp = dot<KPL>(u, p);
+                int sampled = 0;
+                int cur = c0, cur_cn = c0_cn, nxt = c1, nxt_st = c1_st, nxt_cn = c1_cn;
+                while (sampled < m.max_sampled) {
+                    sampled++;
+                    const int slot = (sampled - 1) % FR_RING;
+                    // stages one / two of the next candidates, under this candidate's rows
+                    const int nn = lfm_bounded(next_u32(), (uint32_t)n_items);
+                    int nn_st, nn_cn;
+                    bounds(nn, nn_st, nn_cn);
+                    __syncwarp();
+                    stage_list(nxt, nxt_st, nxt_cn, sampled % FR_RING);
+                    fr_wait1();
+                    __syncwarp();
+                    const int cand = cur;
+                    if (cur_cn >= 0) gather_staged<KPL>(m.item, a.hot_slot_item, d, cur_cn, fr_ring, slot, q, fr_q, lane);
+                    else gather_b<KPL>(a.itf, m.item, a.hot_slot_item, d, cand, q, fr_q, lane);
+                    const float np = dot<KPL>(u, q);
+                    c_neg++;
+                    cur = nxt; cur_cn = nxt_cn;
+                    nxt = nn; nxt_st = nn_st; nxt_cn = nn_cn;
+                    if (np > pp - 1.0f) {
+                        if (lfm_warp_member(a.pos.indices, ps, pe, cand, lane)) { c_rej++; continue; }
+                        loss = fminf(tp.weight * __ldg(a.loss_table_f + sampled), (float)LFM_MAX_LOSS);
+                        neg_id = cand;
+                        updated = true;
+                        break;
+                    }
+                }
+                fr_wait0();  // nothing of this interaction's staging may land in the ring later
+                __syncwarp();
+            } else if (LOSS == LOSS_BPR) {
                 int tries = 0;
                 do {  // T:1123-1127: popularity-weighted draw from the interaction list
                     int64_t j = (int64_t)(((unsigned long long)next_u32() * (unsigned long long)a.n_all) >> 32);
@@ -658,7 +798,7 @@ __global__ void __launch_bounds__(HOT ? 512 : 256) hogwild_kernel(FitArgs a, con
                     c_neg++;
                     if (np > pp - 1.0f) {
                         if (lfm_warp_member(a.pos.indices, ps, pe, cand, lane)) { c_rej++; continue; }
-                        float l = (float)a.loss_table[sampled];
+                        float l = __ldg(a.loss_table_f + sampled);
                         loss = (LOSS == LOSS_KOS) ? l : tp.weight * l;
                         if (loss > (float)LFM_MAX_LOSS) loss = (float)LFM_MAX_LOSS;
                         neg_id = cand;
@@ -798,7 +938,8 @@ cudaError_t launch_generic(const FitArgs& a, const Tuple* tuples, int64_t begin,
                 // hot-row variant: 512-thread CTAs, one per SM (the accumulators take most of the
                 // shared memory), persistent warps
                 auto kern = hogwild_kernel<LOSS, 4, 4, false, false, true>;
-                const size_t smem = (size_t)a.n_hot * ((2 * (m.d >> 2) + 1) * sizeof(float4) + sizeof(int));
+                const size_t smem = (((size_t)a.n_hot * ((2 * (m.d >> 2) + 1) * sizeof(float4) + sizeof(int)) + 15) & ~(size_t)15) +
+                                    (size_t)16 * FR_RING * 32 * sizeof(int2);  // accumulators + locks, then 16 warps' candidate rings
                 cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 int per_sm = 0;
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 512, smem);

@@ -306,14 +306,13 @@ struct FeatRow {
     int cnt;    // number of features (<= 32), or -1 when the row was too long to keep
 };
 
-#define FB 10  // feature rows in flight per batch (C3: identity + up to 8 tags + slack)
+#define FB 4   // feature rows in flight per batch (10 in flight made the kernel twice as large and slower:
+               // profiles/README.md, C3 steps v2-v5)
 
 // Gather in the float4 layout with the row loads of up to FB features in flight at a time
 // (the generic gather walks the features one dependent round trip after the other).
-// (gather_b / scatter_b are deliberately NOT inlined: with three call sites each the kernel was 7 300
-//  instructions and instruction-fetch stalls were its top stall reason, profiles/r2_ncu_c3_hot_v3_summary.txt)
 template <int KPL>
-__device__ __noinline__ void gather_b(const DevCsr& f, const DevTable& t, const int32_t* __restrict__ hot_slot,
+__device__ __forceinline__ void gather_b(const DevCsr& f, const DevTable& t, const int32_t* __restrict__ hot_slot,
                                          int d, int row, Repr<KPL>& r, FeatRow& fr, int lane) {
     constexpr int NCH = KPL / 4;
 #pragma unroll
@@ -387,6 +386,8 @@ __device__ __noinline__ void gather_b(const DevCsr& f, const DevTable& t, const 
 // under the row fetch and scoring of the current one: the row bounds wait in registers, the
 // (feature id, weight) lists stream into a per-warp shared-memory ring with cp.async.
 #define FR_RING 3
+#define FR_STAGED 0  // measured on C3: 301 ms per epoch with the staging vs 247 ms without (the extra
+                     // instructions and the out-of-line gathers cost more than the hidden round trips)
 __device__ __forceinline__ void fr_cp_async4(void* smem, const void* gmem) {
     unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem) : "memory");
@@ -452,9 +453,7 @@ __device__ __noinline__ void gather_staged(const DevTable& t, const int32_t* __r
 // Hot rows go to the CTA's shared-memory accumulator under the slot lock, everything else (and
 // a hot row whose lock is busy) straight to L2.  One float4 chunk per lane (d <= 128); arguments
 // by value so that they stay in registers across the call.
-// (not inlined: it is called from FB unrolled sites per scatter, and the kernel's instruction
-//  footprint was already costing instruction-cache misses: profiles/r2_ncu_c3_hot_v1_summary.txt)
-__device__ __noinline__ void apply_row(float* tw, float* tg, float* tb, float* tbg, float4* hacc, int* hlocks,
+__device__ __forceinline__ void apply_row(float* tw, float* tg, float* tb, float* tbg, float4* hacc, int* hlocks,
                                        int hstride, int d, float lr, int ft, float fw, int hs, float4 g0,
                                        float4 grad, float bgrad, int lane) {
     const int d4 = d >> 2;
@@ -501,7 +500,7 @@ __device__ __noinline__ void apply_row(float* tw, float* tg, float* tb, float* t
 // Adagrad scatter (alpha == 0) in the float4 layout: the accumulator rows of up to FB features
 // are fetched together; `fr` (from the gather of the same row) saves the index loads.
 template <int KPL>
-__device__ __noinline__ void scatter_b(const DevCsr& f, DevTable& t, const int32_t* __restrict__ hot_slot,
+__device__ __forceinline__ void scatter_b(const DevCsr& f, DevTable& t, const int32_t* __restrict__ hot_slot,
                                           const HotSmem& h, const DevModel& m, int row, const FeatRow& fr,
                                           const float (&grad)[KPL], float bgrad, int lane) {
     static_assert(KPL == 4, "the hot-row path holds one float4 chunk per lane (d <= 128)");
@@ -703,7 +702,7 @@ __global__ void __launch_bounds__(HOT ? 512 : 256) hogwild_kernel(FitArgs a, con
                 pp = __shfl_sync(LFM_FULL, my_val, src);
                 GATHER(a.itf, m.item, a.hot_slot_item, pos_id, item_scale, p, fr_p);
                 c_pos++;
-            } else if constexpr (HOT && LOSS == LOSS_WARP) {
+            } else if constexpr (HOT && LOSS == LOSS_WARP && FR_STAGED) {
                 // positive item handled together with the first candidates below
                 c_pos++;
             } else {
@@ -714,7 +713,7 @@ __global__ void __launch_bounds__(HOT ? 512 : 256) hogwild_kernel(FitArgs a, con
 
             int neg_id = -1;
             float loss = 0.0f;
-            if constexpr (HOT && LOSS == LOSS_WARP) {
+            if constexpr (HOT && LOSS == LOSS_WARP && FR_STAGED) {
                 // ---- rank sampling with the candidates' feature lists fetched ahead ----
                 const DevCsr& f = a.itf;
                 auto bounds = [&](int item, int& st, int& cn) {  // stage one (identity: nothing to fetch)

@@ -24,14 +24,27 @@ open(os.path.join(tdir, "test_probe.py"), "w").write('''
 import numpy as np, scipy.sparse as sp
 from lightfm.lightfm import LightFM
 def test_probe():
-    for rep in range(5):
+    import sys, os
+    sys.path.insert(0, os.path.join(os.environ["LFM_ROOT"], "tests"))
+    import helpers as H
+    orc = H.oracle_native()
+    for rep in range(300):
         train = sp.rand(10, 100, format="csr", random_state=42)
         model = LightFM()
         model.fit_partial(train)
         rank_input = sp.csr_matrix(np.ones((10, 100)))
         ranks = model.predict_rank(rank_input, num_threads=2).todense()
         bad = [r for r in range(10) if not np.all(np.sort(ranks[r]) == np.arange(100))]
-        print("rep", rep, "bad rows", bad)
+        arr = {k: getattr(model, k) for k in H.MODEL_ARRAYS}
+        want = np.zeros(1000, np.float32)
+        t32 = sp.csr_matrix(rank_input, dtype=np.float32)
+        orc.predict_ranks(orc.CSRMatrix(sp.identity(100, dtype=np.float32, format="csr")),
+                          orc.CSRMatrix(sp.identity(10, dtype=np.float32, format="csr")), orc.CSRMatrix(t32),
+                          orc.CSRMatrix(sp.csr_matrix((10, 100), dtype=np.float32)), want,
+                          H.holder(orc, arr, H.Hyper(d=10)), 1)
+        mism = int((np.asarray(ranks).ravel() != want).sum())
+        if bad or mism or rep % 50 == 0:
+            print("rep", rep, "bad rows", bad, "mismatches vs oracle", mism)
         for r in bad[:2]:
             s = model.predict(r, np.arange(100, dtype=np.int32))
             row = np.asarray(ranks[r]).ravel()
@@ -45,11 +58,10 @@ def test_probe():
 ''')
 env = dict(os.environ)
 env["PYTHONPATH"] = os.pathsep.join([tmp, ROOT, env.get("PYTHONPATH", "")])
-for label, args in (("probe alone", ["reftests/test_probe.py", "-s"]),
-                    ("test_predict_ranks alone", ["reftests/test_api.py", "-k", "test_predict_ranks"]),
-                    ("whole test_api.py", ["reftests/test_api.py"]),
+env["LFM_ROOT"] = ROOT
+for label, args in (("probe alone (300 random models, ranks vs oracle)", ["reftests/test_probe.py", "-s"]),
                     ("whole test_api.py then probe", ["reftests/test_api.py", "reftests/test_probe.py", "-s"])):
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider"] + args, cwd=tmp, env=env,
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     print("=====", label, "rc", r.returncode)
-    print("\n".join(ln for ln in r.stdout.splitlines() if ln.startswith(("rep", "   row", "FAILED")) or "passed" in ln or "failed" in ln))
+    print("\n".join(ln for ln in r.stdout.splitlines() if "rep " in ln or "   row" in ln or "FAILED" in ln or "passed" in ln or "failed" in ln or "Error" in ln))

@@ -145,6 +145,12 @@ int lfm_set_hot_rows(int enabled);
 /* 0: always use the general replay kernel (the prefetching WARP replay kernel is the default where
  * it applies: identity features, adagrad, alpha == 0); both are bit-equal to the oracle. */
 int lfm_set_replay_fast(int enabled);
+/* 0: BPR / logistic replay epochs walk the list sequentially (replay_kernel) instead of through the
+ * dependency-graph path (many warps, same bits; identity features, alpha == 0); tests / A-B timing. */
+int lfm_set_replay_dataflow(int enabled);
+/* Device time of the last dataflow replay epoch: its schedule kernel and its execute kernel (ms), and
+ * the number of tasks (-1: the schedule declined and the sequential kernel ran). */
+int lfm_last_replay_dataflow(double *schedule_ms, double *execute_ms, int32_t *tasks);
 /* Hogwild slot kernels: 1 (default) = the Adagrad accumulator update is an atomic add that returns
  * the old value and the step is scaled by it (every earlier update of the element is seen, whatever
  * is in flight); 0 = read-then-reduce (round-1 behaviour). */

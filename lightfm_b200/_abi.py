@@ -127,6 +127,8 @@ LIB_ONLY = {
     "lfm_set_rank_groups": (C.c_int, [C.c_int]),
     "lfm_set_atomic_accumulators": (C.c_int, [C.c_int]),
     "lfm_set_replay_fast": (C.c_int, [C.c_int]),
+    "lfm_set_replay_dataflow": (C.c_int, [C.c_int]),
+    "lfm_last_replay_dataflow": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "lfm_set_hot_rows": (C.c_int, [C.c_int]),
     "lfm_plan_table": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "lfm_plan_check_finite": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),

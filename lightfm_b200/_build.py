@@ -23,7 +23,7 @@ SOURCES = [
     ("lfm_hogwild.cu", []),
     ("lfm_host.cu", []),
 ]
-HEADERS = ["lfm_common.cuh", "lfm_hogwild_fast.cuh", "lfm_replay_fast.cuh", os.path.join("..", "..", "include", "lfm_cuda.h")]
+HEADERS = ["lfm_common.cuh", "lfm_hogwild_fast.cuh", "lfm_replay_fast.cuh", "lfm_replay_dataflow.cuh", os.path.join("..", "..", "include", "lfm_cuda.h")]
 
 
 def _nvcc():
@@ -45,18 +45,23 @@ def build(force=False, verbose=False):
     bdir = os.path.join(CSRC, "build")
     os.makedirs(bdir, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
-    objs = []
+    objs, jobs = [], []
     for src, extra in SOURCES:
         s = os.path.join(CSRC, src)
         o = os.path.join(bdir, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
             cmd = [nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
-            r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-            if verbose or r.returncode != 0:
-                sys.stderr.write(r.stdout)
-            if r.returncode != 0:
-                raise RuntimeError("nvcc failed on %s" % src)
+            jobs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = []
+    for src, proc in jobs:  # the translation units compile side by side
+        out, _ = proc.communicate()
+        if verbose or proc.returncode != 0:
+            sys.stderr.write(out)
+        if proc.returncode != 0:
+            failed.append(src)
+    if failed:
+        raise RuntimeError("nvcc failed on %s" % ", ".join(failed))
     if force or _stale(OUT, objs):
         tmp = OUT + ".tmp.%d" % os.getpid()   # link aside, then rename: the library is never half-written
         cmd = [nvcc] + ARCH + ["-shared", "-o", tmp] + objs

@@ -102,6 +102,20 @@ def set_replay_fast(enabled):
     return _lib.lfm_set_replay_fast(int(bool(enabled)))
 
 
+def set_replay_dataflow(enabled):
+    """Replay mode, BPR / logistic with identity features: walk the epoch as a dependency graph on
+    many warps (default on) instead of sequentially; the same bits either way."""
+    return _lib.lfm_set_replay_dataflow(int(bool(enabled)))
+
+
+def last_replay_dataflow():
+    """(schedule kernel ms, execute kernel ms, tasks) of the last dataflow replay epoch."""
+    import ctypes as C
+    a, b, n = C.c_double(0), C.c_double(0), C.c_int32(0)
+    _lib.lfm_last_replay_dataflow(C.byref(a), C.byref(b), C.byref(n))
+    return a.value, b.value, n.value
+
+
 def set_hot_rows(enabled):
     """Feature path: per-CTA shared-memory aggregation of hot feature rows (default on)."""
     return _lib.lfm_set_hot_rows(int(bool(enabled)))

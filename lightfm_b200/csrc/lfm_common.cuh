@@ -93,10 +93,16 @@ struct FitArgs {
     // 1 when every Y and every sample weight equals 1.0f (checked on the device when the inputs
     // are staged): pack_kernel then skips two of its three random reads per interaction.
     int32_t unit_weights;
+    // Replay mode, dataflow path (lfm_replay_dataflow.cuh): device scratch for the task list, the
+    // row version counters and the optional membership bitmap; null / 0 -> sequential replay kernels.
+    void* replay_scratch;
+    size_t replay_scratch_bytes;
 };
 
 // ---- launchers (defined in the .cu files) ------------------------------------
 cudaError_t lfm_launch_replay(int loss, const FitArgs& a, cudaStream_t st);
+// Bytes of FitArgs::replay_scratch the dataflow replay path wants for (loss, a); 0: not applicable.
+size_t lfm_replay_dataflow_scratch_bytes(int loss, const FitArgs& a, int64_t bitmap_limit_bytes);
 cudaError_t lfm_launch_hogwild(int loss, const FitArgs& a, Tuple* tuples, cudaStream_t st,
                                int* launches, cudaEvent_t ev_train_begin, cudaEvent_t ev_train_end);
 cudaError_t lfm_launch_regularize(const DevModel& m, DevScales* scales, cudaStream_t st);

@@ -461,6 +461,14 @@ int run_fit(Staged& st, int mode, uint32_t seed, int* launches) {
         }
         if (a.n > 0) {
             if (!a.shuffle) return fail(LFM_ERR_STATE, "replay mode needs the host shuffle order");
+            // BPR / logistic with identity features: scratch for the dataflow walk (task list, row
+            // versions, membership bitmap); without it the sequential kernels run
+            a.replay_scratch = nullptr;
+            a.replay_scratch_bytes = lfm_replay_dataflow_scratch_bytes(st.loss, a, g_bitmap_limit_bytes.load());
+            if (a.replay_scratch_bytes) {
+                int rc = arena_get("replay.scratch", a.replay_scratch_bytes, &a.replay_scratch);
+                if (rc != LFM_OK) return rc;
+            }
             CU(cudaEventRecord(g_ev[4], g_stream));
             CU(lfm_launch_replay(st.loss, a, g_stream));
             CU(cudaEventRecord(g_ev[5], g_stream));

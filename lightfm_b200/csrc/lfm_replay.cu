@@ -456,13 +456,32 @@ __global__ void regularize_kernel(DevModel m, DevScales* scales) {
 }  // namespace
 
 #include "lfm_replay_fast.cuh"
+#include "lfm_replay_dataflow.cuh"
 
 static std::atomic<int> g_replay_fast{1};
+static std::atomic<int> g_replay_dataflow{1};
 extern "C" int lfm_set_replay_fast(int enabled) { return g_replay_fast.exchange(enabled ? 1 : 0); }
+extern "C" int lfm_set_replay_dataflow(int enabled) { return g_replay_dataflow.exchange(enabled ? 1 : 0); }
+
+// Timing of the last dataflow epoch: schedule kernel, execute kernel (ms), tasks (-1: it declined).
+extern "C" int lfm_last_replay_dataflow(double* schedule_ms, double* execute_ms, int32_t* tasks) {
+    if (schedule_ms) *schedule_ms = g_rdf_ms[0];
+    if (execute_ms) *execute_ms = g_rdf_ms[1];
+    if (tasks) *tasks = g_rdf_tasks;
+    return LFM_OK;
+}
+
+size_t lfm_replay_dataflow_scratch_bytes(int loss, const FitArgs& a, int64_t bitmap_limit_bytes) {
+    if (!g_replay_fast.load() || !g_replay_dataflow.load()) return 0;
+    return rdf_scratch_bytes(loss, a, bitmap_limit_bytes);
+}
 
 cudaError_t lfm_launch_replay(int loss, const FitArgs& a, cudaStream_t st) {
     if (g_replay_fast.load()) {
-        cudaError_t e = lfm_try_launch_replay_fast(loss, a, st);
+        cudaError_t e = g_replay_dataflow.load() ? lfm_try_launch_replay_dataflow(loss, a, st) : cudaErrorNotSupported;
+        if (e != cudaErrorNotSupported) return e;
+        cudaGetLastError();
+        e = lfm_try_launch_replay_fast(loss, a, st);
         if (e != cudaErrorNotSupported) return e;
         cudaGetLastError();
     }

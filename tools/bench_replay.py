@@ -11,8 +11,14 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from lightfm_b200 import _lightfm_fast as fast  # noqa: E402
 from lightfm_b200 import synthetic  # noqa: E402
 
-for name, loss, nu, ni, nnz, d in (("C1", "bpr", 943, 1682, 100_000, 16), ("C2-slice", "warp", 138_493, 26_744, 400_000, 64),
-                                   ("logistic", "logistic", 20_000, 5_000, 300_000, 32)):
+CONFIGS = (("C1", "bpr", 943, 1682, 100_000, 16), ("C2-slice", "warp", 138_493, 26_744, 400_000, 64),
+           ("logistic", "logistic", 20_000, 5_000, 300_000, 32),
+           ("C2-shape-bpr", "bpr", 138_493, 26_744, 2_000_000, 64),
+           ("C5-slice-logistic", "logistic", 100_000, 100_000, 4_000_000, 32))
+only = sys.argv[1].split(",") if len(sys.argv) > 1 else None
+for name, loss, nu, ni, nnz, d in CONFIGS:
+    if only and name not in only:
+        continue
     inter = synthetic.interactions(nu, ni, nnz, seed=1, signed=(loss == "logistic"))
     rs = np.random.RandomState(0)
     st = []
@@ -37,5 +43,6 @@ for name, loss, nu, ni, nnz, d in (("C1", "bpr", 943, 1682, 100_000, 16), ("C2-s
         c = fast.last_counters["fit"]
         if rep == 1:
             general = round(c["positives"] / c["train_kernel_ms"], 1)
-    print(json.dumps({"config": name, "general_kernel_k_interactions_per_s": general, "loss": loss, "d": d, "nnz": inter.nnz, "mode": c["mode"], "replay_kernel_ms": round(c["train_kernel_ms"], 1),
+    df = fast.last_replay_dataflow() if loss in ("bpr", "logistic") else None
+    print(json.dumps({"config": name, "dataflow_schedule_ms_execute_ms_tasks": df, "general_kernel_k_interactions_per_s": general, "loss": loss, "d": d, "nnz": inter.nnz, "mode": c["mode"], "replay_kernel_ms": round(c["train_kernel_ms"], 1),
                       "k_interactions_per_s": round(c["positives"] / c["train_kernel_ms"], 1), "wall_s": round(dt, 3)}), flush=True)

@@ -64,7 +64,7 @@ def test_dataflow_matches_oracle(loss):
 
 @pytest.mark.parametrize("n", (1, 2, 31, 32, 33, 64, 65, 1000))
 def test_chunk_boundaries(n):
-    inter = H.synthetic_interactions(60, 50, n, 7)
+    inter = H.synthetic_interactions(80, 70, n, 7)
     assert inter.nnz == n
     _same("bpr", inter, H.Hyper(d=16), epochs=3)
     _same("logistic", inter, H.Hyper(d=16), epochs=3)

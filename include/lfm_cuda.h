@@ -148,8 +148,8 @@ int lfm_set_replay_fast(int enabled);
 /* 0: BPR / logistic replay epochs walk the list sequentially (replay_kernel) instead of through the
  * dependency-graph path (many warps, same bits; identity features, alpha == 0); tests / A-B timing. */
 int lfm_set_replay_dataflow(int enabled);
-/* Device time of the last dataflow replay epoch: its schedule kernel and its execute kernel (ms), and
- * the number of tasks (-1: the schedule declined and the sequential kernel ran). */
+/* Device time of the last dataflow replay epoch: its scheduler warp (schedule_ms) and the whole kernel
+ * (execute_ms; the two overlap), and the number of tasks. */
 int lfm_last_replay_dataflow(double *schedule_ms, double *execute_ms, int32_t *tasks);
 /* Hogwild slot kernels: 1 (default) = the Adagrad accumulator update is an atomic add that returns
  * the old value and the step is scaled by it (every earlier update of the element is seen, whatever

@@ -109,7 +109,7 @@ def set_replay_dataflow(enabled):
 
 
 def last_replay_dataflow():
-    """(schedule kernel ms, execute kernel ms, tasks) of the last dataflow replay epoch."""
+    """(scheduler warp ms, whole kernel ms, tasks) of the last dataflow replay epoch."""
     import ctypes as C
     a, b, n = C.c_double(0), C.c_double(0), C.c_int32(0)
     _lib.lfm_last_replay_dataflow(C.byref(a), C.byref(b), C.byref(n))

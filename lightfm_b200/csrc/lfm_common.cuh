@@ -105,6 +105,8 @@ cudaError_t lfm_launch_replay(int loss, const FitArgs& a, cudaStream_t st);
 size_t lfm_replay_dataflow_scratch_bytes(int loss, const FitArgs& a, int64_t bitmap_limit_bytes);
 cudaError_t lfm_launch_hogwild(int loss, const FitArgs& a, Tuple* tuples, cudaStream_t st,
                                int* launches, cudaEvent_t ev_train_begin, cudaEvent_t ev_train_end);
+// tuples[i] = {user, item, weight, y}[order[i]]; order = a.shuffle when given, else a Feistel permutation keyed by perm_key
+cudaError_t lfm_launch_pack(const FitArgs& a, int loss, Tuple* tuples, uint32_t perm_key, cudaStream_t st);
 cudaError_t lfm_launch_regularize(const DevModel& m, DevScales* scales, cudaStream_t st);
 // Delta exchange of a replicated table (multi-GPU): up to four (pointer, count)
 // segments -- rows [begin, begin+count) of w, g, b, bg -- addressed as one flat range.

@@ -11,14 +11,17 @@
 // see its rows exactly as the interactions before it (in visiting order) left them, and two
 // interactions that share no row commute exactly (they read and write disjoint addresses).
 //
-//   1. rdf_schedule_kernel (one warp) walks the shuffled list in order.  It consumes the rand_r
-//      stream exactly as the reference does (32 draws speculated per round through an LCG
-//      jump-ahead; a rejected draw re-aligns the round), and gives every interaction a task
-//      {user, item, negative, versions}: `version` of a row = how many earlier interactions touch it.
-//   2. rdf_execute_kernel (all SMs, one warp per task, tasks handed out in visiting order): wait
-//      until the task's rows have reached their versions (ld.acquire spin), run the reference's
-//      arithmetic on them, publish version + 1 (st.release).  The earliest unfinished task never
-//      waits on anything, so the walk always advances (cooperative launch: every warp is resident).
+// One cooperative kernel (rdf_kernel), two roles:
+//   * the SCHEDULER (one warp with an SM to itself) walks the shuffled list in order.  It consumes
+//     the rand_r stream exactly as the reference does (32 draws judged per round -- the state of
+//     draw k is an LCG jump-ahead, the candidates' item ids stream in ahead of time through a
+//     cp.async ring, a rejected draw re-aligns the round) and emits one task per interaction:
+//     {user, item, negative, versions}, `version` of a row = how many earlier interactions touch it;
+//   * the EXECUTORS (every other SM, one warp per task, tasks handed out in visiting order) wait
+//     until the task exists and its rows have reached their versions, run the reference's
+//     arithmetic on them and publish version + 1 (st.release).  The earliest unfinished task never
+//     waits on another task, and the scheduler never waits at all, so the walk always advances
+//     (cooperative launch: every warp is resident).
 //
 // The result equals replay_kernel<BPR / LOGISTIC> bit for bit (tests/test_gpu_replay_dataflow.py),
 // which in turn is the oracle's / the reference's single-thread result.
@@ -27,46 +30,68 @@
 namespace {
 
 struct __align__(16) RdfTask {  // 32 B
-    int32_t user, item, neg;  // neg: BPR only
+    int32_t user, item, neg;  // neg: BPR only; -1 = the kept draw is the positive item itself
     int32_t eu, ei, en;       // versions the user / item / negative rows must have reached
     float weight, y;
 };
 
+// header words (device scratch, zeroed before the launch)
+enum { RDF_H_TOTAL = 0, RDF_H_STALL = 1, RDF_H_PRODUCED = 2, RDF_H_DONE = 3, RDF_H_SCHED_US = 4 };
+
 struct RdfScratch {
-    int32_t* header;   // [0] number of tasks, or -1: not representable (caller runs replay_kernel); [1] stall flag
-    int32_t* cnt_user; // schedule: touches so far            [n_users]
-    int32_t* cnt_item; //                                     [n_items]
-    int32_t* ver_user; // execute: published row versions     [n_users]
-    int32_t* ver_item; //                                     [n_items]
-    RdfTask* tasks;    // [n]
+    int32_t* header;    // see RDF_H_*
+    int32_t* cnt_user;  // scheduler: touches so far             [n_users]   (global fallback)
+    int32_t* cnt_item;  //                                       [n_items]
+    int32_t* ver_user;  // executors: published row versions     [n_users]
+    int32_t* ver_item;  //                                       [n_items]
+    RdfTask* tasks;     // [n]
+    const Tuple* tuples;  // [n] the interactions in visiting order (pack_kernel), user < 0: skipped
     const uint32_t* bitmap;  // optional exact membership bitmap of the positives CSR (else null)
     int32_t bitmap_words;
+    int32_t cnt_in_smem;     // 1: the touch counters live in the scheduler CTA's shared memory
+    uint64_t mod_magic;      // ceil(2^64 / n): draw % n without a division (Lemire 2019)
 };
 
-#define RDF_WARPS 8  // warps per CTA of the execute kernel
-#define RDF_RING 128  // candidate ring entries (schedule kernel)
-#define RDF_AHEAD 96  // draws requested ahead of the one being judged (3 cp.async groups)
+#define RDF_WARPS 8      // warps per CTA
+#define RDF_RING 256     // candidate ring entries (scheduler)
+#define RDF_AHEAD 224    // draws requested ahead of the one being judged (7 cp.async groups)
+#define RDF_PUBLISH 4    // the scheduler publishes its progress every RDF_PUBLISH chunks of 32
+#define RDF_PF 16         // chunks of the packed list prefetched into L2 ahead of the scheduler
 
 __device__ __forceinline__ int rdf_ld_acquire(const int32_t* p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ int rdf_ld_relaxed(const int32_t* p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void rdf_st_release(int32_t* p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ int rdf_ld_volatile(const int32_t* p) {
-    int v;
-    asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+__device__ __forceinline__ unsigned long long rdf_now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
 }
 
-// ---- 1. schedule ---------------------------------------------------------------------------
+// ---- scheduler (one warp) ------------------------------------------------------------------
 template <int LOSS>
-__global__ void __launch_bounds__(32, 1) rdf_schedule_kernel(FitArgs a, RdfScratch s) {
+__device__ __forceinline__ void rdf_schedule(const FitArgs& a, const RdfScratch& s, int32_t* cnt_smem) {
     const int lane = threadIdx.x;
     const unsigned lt = (1u << lane) - 1u;
     const int64_t n = a.n;
+    const unsigned long long t_begin = rdf_now_ns();
+    int32_t* cnt_user = s.cnt_user;
+    int32_t* cnt_item = s.cnt_item;
+    if (s.cnt_in_smem) {
+        cnt_user = cnt_smem;
+        cnt_item = cnt_smem + a.model.user.n;
+        for (int i = lane; i < a.model.user.n + a.model.item.n; i += 32) cnt_smem[i] = 0;
+        __syncwarp();
+    }
     // LCG jump-ahead (rand_r's state update, T:76): lane l holds (A^(l+1), C_(l+1)) with
     // state after l+1 draws = A^(l+1) * state + C_(l+1)
     uint32_t ja = 1103515245u, jc = 12345u;
@@ -74,12 +99,11 @@ __global__ void __launch_bounds__(32, 1) rdf_schedule_kernel(FitArgs a, RdfScrat
         jc = jc * 1103515245u + 12345u;
         ja = ja * 1103515245u;
     }
-    auto jump = [&](uint32_t st, int k) -> uint32_t {  // state after k more draws (0 <= k <= 32)
+    auto jump = [&](uint32_t st, int k) -> uint32_t {  // state after k more draws (0 <= k <= 32), k warp-uniform
         const int src = k > 0 ? k - 1 : 0;
         const uint32_t A = __shfl_sync(LFM_FULL, ja, src), C = __shfl_sync(LFM_FULL, jc, src);
         return k > 0 ? A * st + C : st;
     };
-    uint32_t base = a.seed;  // rand_r state before the next draw (draw number qbase)
     // Candidate ring (BPR): which item a draw names does not depend on who consumes it, so the
     // item_ids loads of the next RDF_AHEAD draws are always in flight (cp.async into shared memory)
     // and only the membership test of a round is a dependent load.
@@ -87,10 +111,11 @@ __global__ void __launch_bounds__(32, 1) rdf_schedule_kernel(FitArgs a, RdfScrat
     uint32_t fbase = a.seed;     // rand_r state before draw number `filled`
     uint32_t filled = 0, qbase = 0;
     auto fetch = [&](int count) {  // lanes < count request the candidates of draws filled + lane
-        const uint32_t st = jump(fbase, lane + 1);
         if (lane < count) {
-            const int r = (int)(lfm_temper(st) >> 1);
-            rp_cp_async4(&ring[(filled + lane) & (RDF_RING - 1)], a.item_ids + (r % (int)n));
+            const uint32_t st = ja * fbase + jc;                 // state after lane + 1 draws
+            const uint32_t r = lfm_temper(st) >> 1;              // rand_r's value (T:77-81)
+            const uint32_t idx = (uint32_t)__umul64hi(s.mod_magic * (uint64_t)r, (uint64_t)n);  // r % n
+            rp_cp_async4(&ring[(filled + lane) & (RDF_RING - 1)], a.item_ids + idx);
         }
         rp_commit();
         fbase = jump(fbase, count);
@@ -100,51 +125,59 @@ __global__ void __launch_bounds__(32, 1) rdf_schedule_kernel(FitArgs a, RdfScrat
         for (int g = 0; g < RDF_AHEAD / 32; g++) fetch(32);
     unsigned long long c_neg = 0, c_rej = 0;
     int out_base = 0;
-    bool bad = false;
 
-    // tuple pipeline: the next chunk's tuples are loaded while this one is scheduled
-    int nrow = 0, nuser = 0, nitem = 0;
-    float ny = 0.f, nw = 0.f;
-    auto load_tuple = [&](int64_t t) {
-        if (t < n) {
-            nrow = a.shuffle[t];
-            nuser = a.user_ids[nrow];
-            nitem = a.item_ids[nrow];
-            ny = a.y[nrow];
-            nw = a.sample_weight[nrow];
-        }
+    // tuple pipeline: the list was packed in visiting order by pack_kernel, so the scheduler streams
+    // it (one 16 B tuple per lane per chunk), two chunks ahead in registers and RDF_PF chunks ahead in L2
+    const int4* tup = (const int4*)s.tuples;
+    auto load_tuple = [&](int64_t t) -> int4 { return t < n ? __ldcg(tup + t) : make_int4(-1, 0, 0, 0); };
+    auto prefetch = [&](int64_t t) {
+        if (t < n && (lane & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(tup + t));
     };
-    load_tuple(lane);
-    for (int64_t t0 = 0; t0 < n; t0 += 32) {
+#pragma unroll 1
+    for (int c = 0; c < RDF_PF; c++) prefetch((int64_t)c * 32 + lane);
+    int4 tp1 = load_tuple(lane), tp2 = load_tuple(32 + lane);
+    int chunk = 0;
+    for (int64_t t0 = 0; t0 < n; t0 += 32, chunk++) {
         const bool in = t0 + lane < n;
-        const int user = nuser, item = nitem;
-        const float y = ny, w = nw;
-        load_tuple(t0 + 32 + lane);
-        const bool valid = in && (LOSS == LOSS_LOGISTIC || y > 0);
+        const int user = tp1.x, item = tp1.y;
+        const float w = __int_as_float(tp1.z), y = __int_as_float(tp1.w);
+        tp1 = tp2;
+        tp2 = load_tuple(t0 + 64 + lane);
+        prefetch(t0 + (int64_t)RDF_PF * 32 + lane);
+        const bool valid = in && user >= 0;  // pack_kernel marks BPR's Y <= 0 interactions (T:1112-1113) with user = -1
         const unsigned V = __ballot_sync(LFM_FULL, valid);
         const int nvalid = __popc(V);
         const int rank = __popc(V & lt);
+        // touch counters of my rows as the earlier chunks left them (independent of the sampling below)
+        int eu = 0, ei = 0, en = 0;
+        if (valid) {
+            eu = cnt_user[user];
+            ei = cnt_item[item];
+        }
         int neg = -1;
         if (LOSS == LOSS_BPR) {
             int ps = 0, pe = 0;
-            if (valid && !s.bitmap) {
-                ps = a.pos.indptr[user];
-                pe = a.pos.indptr[user + 1];
+            const uint32_t* brow = nullptr;
+            if (valid) {
+                if (s.bitmap) {
+                    brow = s.bitmap + (size_t)user * s.bitmap_words;
+                } else {
+                    ps = a.pos.indptr[user];
+                    pe = a.pos.indptr[user + 1];
+                }
             }
             int start = 0;     // valid interactions of this chunk already given their negative
             int attempts = 0;  // draws the interaction at rank == start has already rejected
             while (start < nvalid) {
                 const bool active = valid && rank >= start;
-                const int k = active ? rank - start : 0;  // this lane's draw, counted from base
+                const int k = active ? rank - start : 0;  // this lane's draw, counted from qbase
                 rp_wait<RDF_AHEAD / 32 - 1>();  // the groups holding draws qbase .. qbase + 31 have landed
                 __syncwarp();
                 const int cand = ring[(qbase + (uint32_t)k) & (RDF_RING - 1)];
                 bool mem = false;
                 if (active) {
-                    if (s.bitmap)
-                        mem = (s.bitmap[(size_t)user * s.bitmap_words + (cand >> 5)] >> (cand & 31)) & 1u;
-                    else
-                        mem = lfm_bsearch(a.pos.indices, ps, pe, cand);
+                    if (s.bitmap) mem = (brow[cand >> 5] >> (cand & 31)) & 1u;
+                    else mem = lfm_bsearch(a.pos.indices, ps, pe, cand);
                 }
                 // T:1123-1127: the loop gives up after no_examples draws and keeps the last one
                 const int64_t att = (rank == start) ? attempts : 0;
@@ -161,67 +194,77 @@ __global__ void __launch_bounds__(32, 1) rdf_schedule_kernel(FitArgs a, RdfScrat
                     if (lane == fl) attempts = (rank == start ? attempts : 0) + 1;
                     c_rej++;
                 }
-                const bool accepted = active && rank < f;
-                if (accepted) neg = cand;
-                // a kept draw that IS a positive (the give-up case) may equal the positive item:
-                // not a three-distinct-rows task any more
-                if (__ballot_sync(LFM_FULL, accepted && mem)) bad = true;
+                const bool kept = active && rank < f;
+                if (kept) neg = (cand == item) ? -1 : cand;  // give-up case only: the draw may be the positive itself
+                c_rej += __popc(__ballot_sync(LFM_FULL, kept && mem));  // replay_kernel counts a kept member draw too
                 c_neg += (unsigned long long)consumed;
                 start = f;
-                base = jump(base, consumed);
                 qbase += (uint32_t)consumed;
                 __syncwarp();  // every lane has read its candidate before the ring moves on
                 fetch(consumed);
             }
+            if (valid && neg >= 0) en = cnt_item[neg];
         }
-        // versions: touches of my rows by earlier interactions (earlier chunks: counters; this
-        // chunk: lanes below me)
-        int eu = 0, ei = 0, en = 0;
-        if (valid) {
-            eu = rdf_ld_volatile(s.cnt_user + user);
-            ei = rdf_ld_volatile(s.cnt_item + item);
-            if (LOSS == LOSS_BPR) en = rdf_ld_volatile(s.cnt_item + neg);
+        // versions: + touches by the lanes below me; and am I the last lane of the chunk on each row
+        bool lu = true, li = true, ln = true;
+        {
+            const unsigned gt = ~lt & ~(1u << lane);
+            const unsigned mu = __match_any_sync(LFM_FULL, valid ? user : -1 - lane) & V;  // lanes on my user row
+            eu += __popc(mu & lt);
+            lu = (mu & gt) == 0;
+            if (LOSS == LOSS_LOGISTIC) {
+                const unsigned mi = __match_any_sync(LFM_FULL, valid ? item : -1 - lane) & V;
+                ei += __popc(mi & lt);
+                li = (mi & gt) == 0;
+            }
         }
+        if (LOSS == LOSS_BPR) {
 #pragma unroll 4
-        for (int j = 0; j < 32; j++) {
-            const int uj = __shfl_sync(LFM_FULL, user, j), pj = __shfl_sync(LFM_FULL, item, j);
-            const int nj = __shfl_sync(LFM_FULL, neg, j);
-            if (((V >> j) & 1u) && j < lane && valid) {
-                eu += (uj == user);
-                ei += (pj == item);
-                if (LOSS == LOSS_BPR) {
-                    ei += (nj == item);
-                    en += (pj == neg) + (nj == neg);
+            for (int j = 0; j < 32; j++) {  // an item row is touched as a positive or as a negative
+                const int pj = __shfl_sync(LFM_FULL, item, j), nj = __shfl_sync(LFM_FULL, neg, j);
+                if (((V >> j) & 1u) && valid && j != lane) {
+                    const bool mi = pj == item || nj == item;
+                    const bool mn = neg >= 0 && (pj == neg || nj == neg);
+                    if (j < lane) {
+                        ei += mi; en += mn;
+                    } else {
+                        li = li && !mi; ln = ln && !mn;
+                    }
                 }
             }
         }
         __syncwarp();  // every lane has read the counters before they move
         if (valid) {
-            atomicAdd(s.cnt_user + user, 1);
-            atomicAdd(s.cnt_item + item, 1);
-            if (LOSS == LOSS_BPR) atomicAdd(s.cnt_item + neg, 1);
+            // one store per row: the last lane on it writes the count after this chunk
+            if (lu) cnt_user[user] = eu + 1;
+            if (li) cnt_item[item] = ei + 1;
+            if (LOSS == LOSS_BPR && neg >= 0 && ln) cnt_item[neg] = en + 1;
             RdfTask tk;
             tk.user = user; tk.item = item; tk.neg = neg;
             tk.eu = eu; tk.ei = ei; tk.en = en;
             tk.weight = w; tk.y = y;
             s.tasks[out_base + rank] = tk;
         }
-        __threadfence();
-        __syncwarp();
         out_base += nvalid;
+        __syncwarp();  // counters (same SM: shared memory / L1) and tasks written before the next chunk reads
+        if ((chunk % RDF_PUBLISH) == RDF_PUBLISH - 1 && lane == 0) rdf_st_release(s.header + RDF_H_PRODUCED, out_base);
     }
+    __syncwarp();
     if (lane == 0) {
-        s.header[0] = bad ? -1 : out_base;
         a.scales->item_scale = 1.0;  // alpha == 0: the scales never leave 1
         a.scales->user_scale = 1.0;
         a.counters->positives = (unsigned long long)out_base;
         a.counters->negatives = c_neg;
         a.counters->updates = (unsigned long long)out_base;
         a.counters->rejected = c_rej;
+        s.header[RDF_H_TOTAL] = out_base;
+        s.header[RDF_H_SCHED_US] = (int32_t)((rdf_now_ns() - t_begin) / 1000ull);
+        rdf_st_release(s.header + RDF_H_PRODUCED, out_base);
+        rdf_st_release(s.header + RDF_H_DONE, 1);
     }
 }
 
-// ---- 2. execute ----------------------------------------------------------------------------
+// ---- executors -----------------------------------------------------------------------------
 template <int K, int AD>
 struct RdfRow {
     float w[K], g[K], m[K];
@@ -263,43 +306,71 @@ __device__ __forceinline__ void rdf_store_row(const RdfRow<K, AD>& r, const DevT
     }
 }
 
+__device__ __forceinline__ RdfTask rdf_load_task(const RdfTask* p) {  // L2: the scheduler is still writing the list
+    const int4 x = __ldcg((const int4*)p), y = __ldcg((const int4*)p + 1);
+    RdfTask t;
+    t.user = x.x; t.item = x.y; t.neg = x.z; t.eu = x.w;
+    t.ei = y.x; t.en = y.y; t.weight = __int_as_float(y.z); t.y = __int_as_float(y.w);
+    return t;
+}
+
 template <int LOSS, int K, int AD>
-__global__ void __launch_bounds__(RDF_WARPS * 32) rdf_execute_kernel(FitArgs a, RdfScratch s) {
-    extern __shared__ __align__(16) float rdf_smem[];
+__device__ __forceinline__ void rdf_execute(const FitArgs& a, const RdfScratch& s, float* smem, int e_id, int n_exec) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    DevModel& m = a.model;
+    const DevModel& m = a.model;
     const int d = m.d;
-    float* su = rdf_smem + (size_t)wib * 3 * (d + 1);
+    float* su = smem + (size_t)wib * 3 * (d + 1);
     float* sp = su + (d + 1);
     float* sn = sp + (d + 1);
-    const int n_tasks = s.header[0];  // -1: nothing to do here
-    const int W = gridDim.x * RDF_WARPS;
     const float fw = (float)((double)1.0f * 1.0);  // f32(double(1.0f) * scale), scale == 1
     const double lr = (double)m.lr;
-    const int nwait = LOSS == LOSS_BPR ? 3 : 2;
+    int produced = 0;  // tasks known to exist
 
-    // consecutive tasks go to different SMs: the runnable ones are always the earliest ones
-    int t = wib * gridDim.x + blockIdx.x;
-    RdfTask tk;
-    if (t < n_tasks) tk = s.tasks[t];
-    for (; t < n_tasks; t += W) {
-        RdfTask nx = tk;
-        if (t + W < n_tasks) nx = s.tasks[t + W];
+    for (int t = e_id;; t += n_exec) {
+        // ---- the task exists? ----
+        if (t >= produced) {
+            int go = 1;
+            if (lane == 0) {
+                for (;;) {
+                    produced = rdf_ld_acquire(s.header + RDF_H_PRODUCED);
+                    if (t < produced) break;
+                    if (rdf_ld_acquire(s.header + RDF_H_DONE)) {
+                        produced = rdf_ld_acquire(s.header + RDF_H_PRODUCED);
+                        go = t < produced;
+                        break;
+                    }
+                    // the scheduler emits a task every few tens of ns: sleep roughly until mine is due
+                    const int ahead = t - produced;
+                    __nanosleep(ahead > 200 ? 4000 : 100 + 20 * ahead);
+                }
+            }
+            go = __shfl_sync(LFM_FULL, go, 0);
+            produced = __shfl_sync(LFM_FULL, produced, 0);
+            if (!go) return;
+        }
+        const RdfTask tk = rdf_load_task(s.tasks + t);
+        const bool same = LOSS == LOSS_BPR && tk.neg < 0;  // the kept draw is the positive item itself
+        const int nwait = (LOSS == LOSS_BPR && !same) ? 3 : 2;
+        // ---- its rows are as the earlier tasks left them? ----
         if (lane < nwait) {
             const int32_t* p = lane == 0 ? s.ver_user + tk.user : (lane == 1 ? s.ver_item + tk.item : s.ver_item + tk.neg);
             const int e = lane == 0 ? tk.eu : (lane == 1 ? tk.ei : tk.en);
             // a version that never arrives would be a scheduling bug: give up loudly, not forever
-            for (unsigned spins = 0; rdf_ld_acquire(p) != e; spins++)
+            for (unsigned spins = 0; rdf_ld_relaxed(p) != e; spins++)
                 if (spins > (1u << 23)) {
-                    atomicExch(s.header + 1, 1);
+                    atomicExch(s.header + RDF_H_STALL, 1);
                     break;
                 }
+            __threadfence();  // acquire: the row loads below come after the version that was seen
         }
         __syncwarp();
         RdfRow<K, AD> U, P, N;
         rdf_load_row<K, AD>(U, m.user, tk.user, d, lane);
         rdf_load_row<K, AD>(P, m.item, tk.item, d, lane);
-        if (LOSS == LOSS_BPR) rdf_load_row<K, AD>(N, m.item, tk.neg, d, lane);
+        if (LOSS == LOSS_BPR) {
+            if (same) N = P;
+            else rdf_load_row<K, AD>(N, m.item, tk.neg, d, lane);
+        }
         // representations (T:302-317 with the single identity feature): 0.0f + fw * E
 #pragma unroll
         for (int k = 0; k < K; k++) {
@@ -320,9 +391,13 @@ __global__ void __launch_bounds__(RDF_WARPS * 32) rdf_execute_kernel(FitArgs a, 
             const double pp = (double)score(su, sp, d);
             const double np = (double)score(su, sn, d);
             const double loss = (double)tk.weight * (1.0 - (double)sigmoid_ref((float)(pp - np)));  // T:1160-1165
-            // warp_update (T:537-649): biases, then per component positive / negative / user
-            if (lane == 0) step(&P.b, &P.bg, &P.bm, (double)1.0f, -loss, AD, lr, 0.0, m.rho, m.eps);
-            if (lane == 1) step(&N.b, &N.bg, &N.bm, (double)1.0f, loss, AD, lr, 0.0, m.rho, m.eps);
+            // warp_update (T:537-649): biases, then per component positive / negative / user.  With
+            // negative == positive the two steps hit the same element one after the other.
+            if (lane == 0) {
+                step(&P.b, &P.bg, &P.bm, (double)1.0f, -loss, AD, lr, 0.0, m.rho, m.eps);
+                if (same) step(&P.b, &P.bg, &P.bm, (double)1.0f, loss, AD, lr, 0.0, m.rho, m.eps);
+            }
+            if (lane == 1 && !same) step(&N.b, &N.bg, &N.bm, (double)1.0f, loss, AD, lr, 0.0, m.rho, m.eps);
             if (lane == 2) step(&U.b, &U.bg, &U.bm, (double)1.0f, loss, AD, lr, 0.0, m.rho, m.eps);
 #pragma unroll
             for (int k = 0; k < K; k++) {
@@ -330,13 +405,14 @@ __global__ void __launch_bounds__(RDF_WARPS * 32) rdf_execute_kernel(FitArgs a, 
                 if (j < d) {
                     const float uc = su[j], pc = sp[j], nc = sn[j];
                     step(&P.w[k], &P.g[k], &P.m[k], (double)1.0f, (-loss) * (double)uc, AD, lr, 0.0, m.rho, m.eps);
-                    step(&N.w[k], &N.g[k], &N.m[k], (double)1.0f, loss * (double)uc, AD, lr, 0.0, m.rho, m.eps);
+                    if (same) step(&P.w[k], &P.g[k], &P.m[k], (double)1.0f, loss * (double)uc, AD, lr, 0.0, m.rho, m.eps);
+                    else step(&N.w[k], &N.g[k], &N.m[k], (double)1.0f, loss * (double)uc, AD, lr, 0.0, m.rho, m.eps);
                     step(&U.w[k], &U.g[k], &U.m[k], (double)1.0f, loss * (double)(float)(nc - pc), AD, lr, 0.0,
                          m.rho, m.eps);
                 }
             }
             rdf_store_row<K, AD>(P, m.item, tk.item, d, lane, 0);
-            rdf_store_row<K, AD>(N, m.item, tk.neg, d, lane, 1);
+            if (!same) rdf_store_row<K, AD>(N, m.item, tk.neg, d, lane, 1);
             rdf_store_row<K, AD>(U, m.user, tk.user, d, lane, 2);
         } else {
             const double prediction = (double)sigmoid_ref(score(su, sp, d));  // T:745-760
@@ -357,15 +433,28 @@ __global__ void __launch_bounds__(RDF_WARPS * 32) rdf_execute_kernel(FitArgs a, 
             rdf_store_row<K, AD>(P, m.item, tk.item, d, lane, 0);
             rdf_store_row<K, AD>(U, m.user, tk.user, d, lane, 1);
         }
-        __threadfence();  // this lane's stores are visible device-wide ...
-        __syncwarp();     // ... for every lane, before the versions move
+        __syncwarp();  // every lane's row stores are ordered before the releases below (cumulative)
         if (lane < nwait) {
             int32_t* p = lane == 0 ? s.ver_user + tk.user : (lane == 1 ? s.ver_item + tk.item : s.ver_item + tk.neg);
             const int e = lane == 0 ? tk.eu : (lane == 1 ? tk.ei : tk.en);
             rdf_st_release(p, e + 1);
         }
-        tk = nx;
     }
+}
+
+// CTA 0: its first warp is the scheduler (the rest of that SM stays idle so that the one
+// sequential warp of the epoch owns the SM's issue slots); every other CTA: RDF_WARPS executors.
+template <int LOSS, int K, int AD>
+__global__ void __launch_bounds__(RDF_WARPS * 32) rdf_kernel(FitArgs a, RdfScratch s) {
+    extern __shared__ __align__(16) float rdf_smem[];
+    if (blockIdx.x == 0) {
+        if (threadIdx.x < 32) rdf_schedule<LOSS>(a, s, (int32_t*)rdf_smem);
+        return;
+    }
+    // consecutive tasks go to different SMs: the runnable ones are always the earliest ones
+    const int n_exec = ((int)gridDim.x - 1) * RDF_WARPS;
+    const int e_id = (int)(threadIdx.x >> 5) * ((int)gridDim.x - 1) + ((int)blockIdx.x - 1);
+    rdf_execute<LOSS, K, AD>(a, s, rdf_smem, e_id, n_exec);
 }
 
 }  // namespace
@@ -377,7 +466,8 @@ static size_t rdf_scratch_bytes(int loss, const FitArgs& a, int64_t bitmap_limit
         a.user_alpha != 0.0 || m.d > 256 || m.d < 1 || a.n > 0x7fffffffLL || a.n < 1)
         return 0;
     if (loss == LOSS_BPR && !a.pos.indptr) return 0;
-    size_t b = 256 + sizeof(int32_t) * 2 * ((size_t)m.user.n + (size_t)m.item.n + 64) + sizeof(RdfTask) * (size_t)a.n + 256;
+    size_t b = 256 + sizeof(int32_t) * 2 * ((size_t)m.user.n + (size_t)m.item.n + 64) +
+               (sizeof(RdfTask) + sizeof(Tuple)) * (size_t)a.n + 1024;
     if (loss == LOSS_BPR) {
         const size_t words = ((size_t)a.pos.cols + 31) / 32;
         const size_t bm = sizeof(uint32_t) * words * (size_t)a.pos.rows;
@@ -386,15 +476,15 @@ static size_t rdf_scratch_bytes(int loss, const FitArgs& a, int64_t bitmap_limit
     return b;
 }
 
-// Returns cudaErrorNotSupported when the epoch has to run in replay_kernel instead (out of scope,
-// or the schedule found the one case it does not represent); nothing has been modified then.
-static cudaEvent_t g_rdf_ev[3] = {nullptr, nullptr, nullptr};
-static double g_rdf_ms[2] = {0.0, 0.0};  // schedule kernel, execute kernel of the last dataflow epoch
+static cudaEvent_t g_rdf_ev[2] = {nullptr, nullptr};
+static double g_rdf_ms[2] = {0.0, 0.0};  // scheduler warp, whole kernel of the last dataflow epoch
 static int g_rdf_tasks = -1;
 
+// Returns cudaErrorNotSupported when the epoch has to run in replay_kernel instead (out of scope);
+// nothing has been modified then.
 static cudaError_t lfm_try_launch_replay_dataflow(int loss, const FitArgs& a, cudaStream_t st) {
     if (!a.replay_scratch || a.replay_scratch_bytes == 0) return cudaErrorNotSupported;
-    for (int i = 0; i < 3; i++)
+    for (int i = 0; i < 2; i++)
         if (!g_rdf_ev[i]) {
             cudaError_t ee = cudaEventCreate(&g_rdf_ev[i]);
             if (ee != cudaSuccess) return ee;
@@ -402,6 +492,11 @@ static cudaError_t lfm_try_launch_replay_dataflow(int loss, const FitArgs& a, cu
     const DevModel& m = a.model;
     const int d = m.d;
     const size_t nu = (size_t)m.user.n, ni = (size_t)m.item.n;
+    int dev = 0, sms = 0, coop = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    if (!coop || sms < 2) return cudaErrorNotSupported;
     unsigned char* base = (unsigned char*)a.replay_scratch;
     RdfScratch s;
     s.header = (int32_t*)base;
@@ -414,9 +509,18 @@ static cudaError_t lfm_try_launch_replay_dataflow(int loss, const FitArgs& a, cu
     s.tasks = (RdfTask*)(base + off);
     off += sizeof(RdfTask) * (size_t)a.n;
     off = (off + 255) & ~(size_t)255;
+    Tuple* tuples = (Tuple*)(base + off);
+    s.tuples = tuples;
+    off += sizeof(Tuple) * (size_t)a.n;
+    off = (off + 255) & ~(size_t)255;
     s.bitmap = nullptr;
     s.bitmap_words = 0;
+    s.mod_magic = ~0ull / (uint64_t)a.n + 1ull;
+    const size_t cnt_bytes = sizeof(int32_t) * (nu + ni);
+    s.cnt_in_smem = cnt_bytes <= 160 * 1024 ? 1 : 0;
     cudaError_t e = cudaMemsetAsync(base, 0, 256 + sizeof(int32_t) * 2 * (nu + ni + 64), st);
+    if (e != cudaSuccess) return e;
+    e = lfm_launch_pack(a, loss, tuples, 0u, st);  // the host shuffle order (a.shuffle), Y <= 0 marked for BPR
     if (e != cudaSuccess) return e;
     if (loss == LOSS_BPR) {
         const size_t words = ((size_t)a.pos.cols + 31) / 32;
@@ -428,28 +532,24 @@ static cudaError_t lfm_try_launch_replay_dataflow(int loss, const FitArgs& a, cu
             s.bitmap_words = (int32_t)words;
         }
     }
-    cudaEventRecord(g_rdf_ev[0], st);
-    if (loss == LOSS_BPR) rdf_schedule_kernel<LOSS_BPR><<<1, 32, 0, st>>>(a, s);
-    else rdf_schedule_kernel<LOSS_LOGISTIC><<<1, 32, 0, st>>>(a, s);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    cudaEventRecord(g_rdf_ev[1], st);
-
-    const size_t smem = sizeof(float) * 3 * (d + 1) * RDF_WARPS;
-    int dev = 0, sms = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    size_t smem = sizeof(float) * 3 * (d + 1) * RDF_WARPS;
+    if (s.cnt_in_smem && cnt_bytes > smem) smem = cnt_bytes;
     void* args[2] = {(void*)&a, (void*)&s};
+    cudaEventRecord(g_rdf_ev[0], st);
 #define RDF_LAUNCH(L, KK, AA)                                                                              \
     do {                                                                                                   \
-        auto kern = rdf_execute_kernel<L, KK, AA>;                                                         \
+        auto kern = rdf_kernel<L, KK, AA>;                                                                 \
+        if (smem > 48 * 1024) {                                                                            \
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+            if (e != cudaSuccess) return e;                                                                \
+        }                                                                                                  \
         int per_sm = 0;                                                                                    \
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RDF_WARPS * 32, smem);            \
         if (e != cudaSuccess) return e;                                                                    \
         if (per_sm < 1) return cudaErrorNotSupported;                                                      \
-        if (per_sm > 2) per_sm = 2; /* a few thousand warps: far more than the graph is wide */            \
-        int64_t blocks = (int64_t)per_sm * sms;                                                            \
-        const int64_t need = (a.n + RDF_WARPS - 1) / RDF_WARPS;                                            \
+        /* one CTA per SM: ~1200 warps, far more than the graph is wide; CTA 0 = the scheduler */          \
+        int64_t blocks = sms;                                                                              \
+        const int64_t need = 1 + (a.n + RDF_WARPS - 1) / RDF_WARPS;                                        \
         if (blocks > need) blocks = need;                                                                  \
         e = cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)blocks), dim3(RDF_WARPS * 32), args, \
                                         smem, st);                                                         \
@@ -471,21 +571,17 @@ static cudaError_t lfm_try_launch_replay_dataflow(int loss, const FitArgs& a, cu
 #undef RDF_BY_K
 #undef RDF_LAUNCH
     if (e != cudaSuccess) return e;
-    cudaEventRecord(g_rdf_ev[2], st);
-    // the schedule's verdict (one int): -1 means it met the give-up case of T:1123-1127 and the
-    // execute kernel did nothing
-    int32_t hdr[2] = {0, 0};
+    cudaEventRecord(g_rdf_ev[1], st);
+    int32_t hdr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     e = cudaMemcpyAsync(hdr, s.header, sizeof(hdr), cudaMemcpyDeviceToHost, st);
     if (e != cudaSuccess) return e;
     e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return e;
-    if (hdr[1] != 0) return cudaErrorLaunchTimeout;  // a task waited for a version that never came
-    const int32_t verdict = hdr[0];
-    float ms0 = 0.f, ms1 = 0.f;
-    cudaEventElapsedTime(&ms0, g_rdf_ev[0], g_rdf_ev[1]);
-    cudaEventElapsedTime(&ms1, g_rdf_ev[1], g_rdf_ev[2]);
-    g_rdf_ms[0] = ms0;
-    g_rdf_ms[1] = ms1;
-    g_rdf_tasks = verdict;
-    return verdict < 0 ? cudaErrorNotSupported : cudaSuccess;
+    if (hdr[RDF_H_STALL] != 0) return cudaErrorLaunchTimeout;  // a task waited for a version that never came
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, g_rdf_ev[0], g_rdf_ev[1]);
+    g_rdf_ms[0] = hdr[RDF_H_SCHED_US] / 1000.0;
+    g_rdf_ms[1] = ms;
+    g_rdf_tasks = hdr[RDF_H_TOTAL];
+    return cudaSuccess;
 }

@@ -82,6 +82,15 @@ def test_heavy_rejection_and_long_chains():
     _same("logistic", inter, H.Hyper(d=32), epochs=3)
 
 
+def test_give_up_case_negative_equals_positive():
+    """Every item is a positive of every user: each BPR draw is rejected until the loop gives up after
+    no_examples draws and keeps the last one -- possibly the positive item itself (T:1123-1127)."""
+    inter = sp.coo_matrix(np.ones((2, 3), np.float32))
+    _same("bpr", inter, H.Hyper(d=16), epochs=3)
+    inter = sp.coo_matrix(np.ones((3, 1), np.float32))
+    _same("bpr", inter, H.Hyper(d=16), epochs=2)
+
+
 def test_skipped_interactions_and_sample_weights():
     """BPR skips Y <= 0 without drawing (T:1112-1113); weights scale the loss."""
     inter = H.synthetic_interactions(200, 150, 5000, 9, signed=True)

@@ -44,5 +44,5 @@ for name, loss, nu, ni, nnz, d in CONFIGS:
         if rep == 1:
             general = round(c["positives"] / c["train_kernel_ms"], 1)
     df = fast.last_replay_dataflow() if loss in ("bpr", "logistic") else None
-    print(json.dumps({"config": name, "dataflow_schedule_ms_execute_ms_tasks": df, "general_kernel_k_interactions_per_s": general, "loss": loss, "d": d, "nnz": inter.nnz, "mode": c["mode"], "replay_kernel_ms": round(c["train_kernel_ms"], 1),
+    print(json.dumps({"config": name, "dataflow_scheduler_ms_kernel_ms_tasks": df, "general_kernel_k_interactions_per_s": general, "loss": loss, "d": d, "nnz": inter.nnz, "mode": c["mode"], "replay_kernel_ms": round(c["train_kernel_ms"], 1),
                       "k_interactions_per_s": round(c["positives"] / c["train_kernel_ms"], 1), "wall_s": round(dt, 3)}), flush=True)

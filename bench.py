@@ -22,6 +22,10 @@ step    : one epoch = one pass of fit_warp over the 20 M interactions
          box's host cores; held-out precision@10 / AUC of both weight sets on the 1 % test split
          (same evaluator), and the reference's rate as the CPU baseline (rank 0, N=1)
 
+`c4`, `ranks`, `replay`  extra blocks: BASELINE config 4 on this many GPUs, predict_ranks / fused evaluation /
+         top-k on a C5 slice, and replay mode (num_threads=1: C1 BPR, C5-slice logistic) against the
+         reference's single thread
+
 --impl reference times the unmodified reference (oracle/_ref, rebuilt -march=native for this
 host) through its native entry point on all 20 M interactions per step.
 """
@@ -495,6 +499,19 @@ def run_ours(args):
         except Exception as exc:  # pragma: no cover
             ranks = {"error": "%s: %s" % (type(exc).__name__, exc)}
 
+    replay = None
+    if not args.no_replay:
+        try:
+            fast.release_cache()
+            fast.set_mode("auto")
+            replay = replay_block(fast, with_cpu=not args.no_cpu_baseline)
+            launches += 2 * 2 * 3
+        except Exception as exc:  # pragma: no cover
+            replay = {"error": "%s: %s" % (type(exc).__name__, exc)}
+        finally:
+            fast.set_mode("hogwild")
+            fast.release_cache()
+
     mean = lambda k: sum(c[k] for c in counters) / len(counters)
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
@@ -517,6 +534,7 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "c4": c4,
         "ranks": ranks,
+        "replay": replay,
     }
     print(json.dumps(out))
 
@@ -617,6 +635,78 @@ def ranks_block(fast, with_cpu=True):
     return out
 
 
+def replay_block(fast, with_cpu=True):
+    """Replay mode (num_threads=1, the class default): BASELINE configs[0] = C1 (ML-100k-shaped,
+    BPR, d=16, one thread) and a slice of C5 (logistic, d=32).  Ours: the dependency-graph replay
+    kernel through the boundary call; reference: its own native fit_* at ONE thread on this host.
+    Both start from the same weights, shuffle and rand_r seed; the weights are compared afterwards."""
+    from lightfm_b200 import synthetic
+    ref_fast = None
+    if with_cpu:
+        try:
+            ref_fast, _ = load_reference_native()
+        except Exception:
+            ref_fast = None
+    out = {}
+    for name, loss, nu, ni, nnz, d in (("c1_bpr_d16", "bpr", 943, 1682, 100_000, 16),
+                                       ("c5_slice_logistic_d32", "logistic", 100_000, 100_000, 4_000_000, 32)):
+        inter = synthetic.interactions(nu, ni, nnz, seed=1, signed=(loss == "logistic"))
+        itf = sp.identity(ni, dtype=np.float32, format="csr")
+        usf = sp.identity(nu, dtype=np.float32, format="csr")
+        pos = inter.tocsr()
+        pos.sort_indices()
+        rs0 = np.random.RandomState(0)
+        shuffle = np.arange(inter.nnz, dtype=np.int32)
+        rs0.shuffle(shuffle)
+        w = inter.data if loss != "logistic" else np.ones_like(inter.data)
+
+        def fresh():
+            st = []
+            r = np.random.RandomState(3)
+            for n in (ni, nu):
+                emb = ((r.rand(n, d) - 0.5) / d).astype(np.float32)
+                st += [emb, np.ones_like(emb), np.zeros_like(emb), np.zeros(n, np.float32), np.ones(n, np.float32),
+                       np.zeros(n, np.float32)]
+            return st
+
+        def epoch(api, st, threads=1):
+            h = api.FastLightFM(*st, d, 0, 0.05, 0.95, 1e-6, 10)
+            t0 = time.perf_counter()
+            if loss == "logistic":
+                api.fit_logistic(api.CSRMatrix(itf), api.CSRMatrix(usf), inter.row, inter.col, inter.data, w, shuffle,
+                                 h, 0.05, 0.0, 0.0, threads)
+            else:
+                api.fit_bpr(api.CSRMatrix(itf), api.CSRMatrix(usf), api.CSRMatrix(pos), inter.row, inter.col,
+                            inter.data, w, shuffle, h, 0.05, 0.0, 0.0, threads, np.random.RandomState(11))
+            return time.perf_counter() - t0
+
+        epoch(fast, fresh())                      # warm-up (allocations, module load)
+        st_gpu = fresh()
+        wall = epoch(fast, st_gpu)
+        c = fast.last_counters["fit"]
+        sched_ms, kernel_ms, tasks = fast.last_replay_dataflow()
+        blk = {"workload": "%d x %d, %d interactions, %s, d=%d, num_threads=1 (replay mode: the reference's "
+                           "single-thread result)" % (nu, ni, inter.nnz, loss, d),
+               "interactions_per_s_kernel": c["positives"] / (c["train_kernel_ms"] / 1e3),
+               "interactions_per_s_call": c["positives"] / wall, "kernel_ms": c["train_kernel_ms"],
+               "scheduler_warp_ms": sched_ms, "tasks": tasks, "mode": c["mode"],
+               "call": "lightfm_b200._lightfm_fast.fit_%s(host buffers, num_threads=1)" % loss}
+        if ref_fast is not None:
+            st_ref = fresh()
+            dt = epoch(ref_fast, st_ref)
+            blk["cpu_baseline"] = {"value": inter.nnz / dt, "unit": UNIT, "cores": 1, "kind": "reference",
+                                   "sample": "the reference's native fit_%s on all %d interactions, 1 thread" % (loss, inter.nnz)}
+            worst = 0.0
+            for a_, b_ in zip(st_gpu, st_ref):
+                den = max(float(np.abs(b_).max()), 1e-12)
+                worst = max(worst, float(np.abs(a_.astype(np.float64) - b_).max()) / den)
+            blk["max_weight_diff_vs_reference_rel_to_array_scale"] = worst
+            blk["parity_note"] = ("same weights, shuffle and rand_r seed on both sides; this reference build uses its shipped "
+                                  "-ffast-math flags, the IEEE build is matched to <= 1e-6 in tests/test_gpu_replay_*.py")
+        out[name] = blk
+    return out
+
+
 def holder_for(api, st, d):
     return api.FastLightFM(*st, d, 0, 0.05, 0.95, 1e-6, 10)
 
@@ -684,6 +774,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c4", action="store_true", help="skip the C4 (10M x 1M, 500M nnz) block")
     ap.add_argument("--no-ranks", action="store_true", help="skip the predict_ranks block")
+    ap.add_argument("--no-replay", action="store_true", help="skip the replay-mode (num_threads=1) block")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -49,12 +49,16 @@ struct RdfScratch {
     const uint32_t* bitmap;  // optional exact membership bitmap of the positives CSR (else null)
     int32_t bitmap_words;
     int32_t cnt_in_smem;     // 1: the touch counters live in the scheduler CTA's shared memory
+    int32_t bitmap_in_smem;  // 1: ... and a copy of the bitmap behind them
     uint64_t mod_magic;      // ceil(2^64 / n): draw % n without a division (Lemire 2019)
 };
 
 #define RDF_WARPS 8      // warps per CTA
 #define RDF_RING 256     // candidate ring entries (scheduler)
 #define RDF_AHEAD 224    // draws requested ahead of the one being judged (7 cp.async groups)
+#define RDF_W 8          // draws judged per interaction per round
+#define RDF_WAIT 4       // cp.async groups that may still be in flight when a round reads the ring:
+                         // a round consumes <= 32 + W draws and reads < qbase + 32 + W, (RDF_WAIT + 1) * 40 <= RDF_AHEAD
 #define RDF_PUBLISH 4    // the scheduler publishes its progress every RDF_PUBLISH chunks of 32
 #define RDF_PF 16         // chunks of the packed list prefetched into L2 ahead of the scheduler
 
@@ -92,6 +96,15 @@ __device__ __forceinline__ void rdf_schedule(const FitArgs& a, const RdfScratch&
         for (int i = lane; i < a.model.user.n + a.model.item.n; i += 32) cnt_smem[i] = 0;
         __syncwarp();
     }
+    // membership bitmap: a copy in shared memory when the host found room for it
+    const uint32_t* bitmap = s.bitmap;
+    if (LOSS == LOSS_BPR && s.bitmap && s.bitmap_in_smem) {
+        uint32_t* sb = (uint32_t*)(cnt_smem + (s.cnt_in_smem ? a.model.user.n + a.model.item.n : 0));
+        const int total = a.pos.rows * s.bitmap_words;
+        for (int i = lane; i < total; i += 32) sb[i] = s.bitmap[i];
+        __syncwarp();
+        bitmap = sb;
+    }
     // LCG jump-ahead (rand_r's state update, T:76): lane l holds (A^(l+1), C_(l+1)) with
     // state after l+1 draws = A^(l+1) * state + C_(l+1)
     uint32_t ja = 1103515245u, jc = 12345u;
@@ -110,15 +123,19 @@ __device__ __forceinline__ void rdf_schedule(const FitArgs& a, const RdfScratch&
     __shared__ int ring[RDF_RING];
     uint32_t fbase = a.seed;     // rand_r state before draw number `filled`
     uint32_t filled = 0, qbase = 0;
-    auto fetch = [&](int count) {  // lanes < count request the candidates of draws filled + lane
-        if (lane < count) {
-            const uint32_t st = ja * fbase + jc;                 // state after lane + 1 draws
-            const uint32_t r = lfm_temper(st) >> 1;              // rand_r's value (T:77-81)
-            const uint32_t idx = (uint32_t)__umul64hi(s.mod_magic * (uint64_t)r, (uint64_t)n);  // r % n
-            rp_cp_async4(&ring[(filled + lane) & (RDF_RING - 1)], a.item_ids + idx);
+    auto fetch = [&](int count) {  // request the candidates of draws filled .. filled + count - 1 (count <= 64): one group
+        const uint32_t f32 = jump(fbase, count > 32 ? 32 : 0);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            if (lane + 32 * h < count) {
+                const uint32_t st = ja * (h ? f32 : fbase) + jc;     // state after lane + 32 h + 1 draws
+                const uint32_t r = lfm_temper(st) >> 1;              // rand_r's value (T:77-81)
+                const uint32_t idx = (uint32_t)__umul64hi(s.mod_magic * (uint64_t)r, (uint64_t)n);  // r % n
+                rp_cp_async4(&ring[(filled + lane + 32 * h) & (RDF_RING - 1)], a.item_ids + idx);
+            }
         }
         rp_commit();
-        fbase = jump(fbase, count);
+        fbase = jump(count > 32 ? f32 : fbase, count > 32 ? count - 32 : count);
         filled += (uint32_t)count;
     };
     if (LOSS == LOSS_BPR && n > 0)
@@ -159,8 +176,8 @@ __device__ __forceinline__ void rdf_schedule(const FitArgs& a, const RdfScratch&
             int ps = 0, pe = 0;
             const uint32_t* brow = nullptr;
             if (valid) {
-                if (s.bitmap) {
-                    brow = s.bitmap + (size_t)user * s.bitmap_words;
+                if (bitmap) {
+                    brow = bitmap + (size_t)user * s.bitmap_words;
                 } else {
                     ps = a.pos.indptr[user];
                     pe = a.pos.indptr[user + 1];
@@ -168,39 +185,74 @@ __device__ __forceinline__ void rdf_schedule(const FitArgs& a, const RdfScratch&
             }
             int start = 0;     // valid interactions of this chunk already given their negative
             int attempts = 0;  // draws the interaction at rank == start has already rejected
+            // One round judges RDF_W consecutive draws per interaction: lane r (counted from `start`)
+            // would take draw r if nobody before it rejected anything, draw r + s after s rejections.
+            // Its membership bits for draws r .. r + W - 1 give f_r(s) = the shift it passes on (s plus
+            // its own rejections), and the shifts are then resolved lane after lane.  A chunk is done
+            // in one round unless more than W - 1 rejections pile up before some lane.
             while (start < nvalid) {
                 const bool active = valid && rank >= start;
-                const int k = active ? rank - start : 0;  // this lane's draw, counted from qbase
-                rp_wait<RDF_AHEAD / 32 - 1>();  // the groups holding draws qbase .. qbase + 31 have landed
+                const int k0 = active ? rank - start : 0;
+                rp_wait<RDF_WAIT>();  // the groups holding draws qbase .. qbase + 31 + W have landed
                 __syncwarp();
-                const int cand = ring[(qbase + (uint32_t)k) & (RDF_RING - 1)];
-                bool mem = false;
+                unsigned M = 0;  // bit j: draw k0 + j names one of my positives
                 if (active) {
-                    if (s.bitmap) mem = (brow[cand >> 5] >> (cand & 31)) & 1u;
-                    else mem = lfm_bsearch(a.pos.indices, ps, pe, cand);
+#pragma unroll
+                    for (int j = 0; j < RDF_W; j++) {
+                        const int cand = ring[(qbase + (uint32_t)(k0 + j)) & (RDF_RING - 1)];
+                        bool mem;
+                        if (brow) mem = (brow[cand >> 5] >> (cand & 31)) & 1u;
+                        else mem = lfm_bsearch(a.pos.indices, ps, pe, cand);
+                        M |= (mem ? 1u : 0u) << j;
+                    }
                 }
-                // T:1123-1127: the loop gives up after no_examples draws and keeps the last one
-                const int64_t att = (rank == start) ? attempts : 0;
-                const bool rej = active && mem && att < n - 1;
-                const unsigned R = __ballot_sync(LFM_FULL, rej);
-                int consumed, f;
-                if (R == 0) {
-                    f = nvalid;
-                    consumed = nvalid - start;
+                // T:1123-1127: the loop gives up after no_examples draws and keeps the last one, so a
+                // member draw is a rejection only while fewer than n - 1 draws were rejected before it
+                int64_t lim64 = n - 1 - ((rank == start) ? attempts : 0);
+                const int lim = lim64 > 64 ? 64 : (lim64 < 0 ? 0 : (int)lim64);
+                unsigned table = 0;  // 4 bits per incoming shift s: outgoing shift, 15 = beyond the window
+#pragma unroll
+                for (int sft = 0; sft < RDF_W; sft++) {
+                    const int run = __ffs(~(M >> sft)) - 1;  // consecutive member draws from draw k0 + sft
+                    const int rr = run < lim ? run : lim;
+                    table |= (unsigned)(sft + rr <= RDF_W - 1 ? sft + rr : 15) << (4 * sft);
+                }
+                const unsigned A = __ballot_sync(LFM_FULL, active);
+                int sft = 0, my_in = 0, over_lane = -1, over_s = 0;
+#pragma unroll 4
+                for (int j = 0; j < 32; j++) {
+                    const unsigned tj = __shfl_sync(LFM_FULL, table, j);
+                    if (((A >> j) & 1u) && over_lane < 0) {
+                        if (j == lane) my_in = sft;
+                        const int v = (int)((tj >> (4 * sft)) & 15u);
+                        if (v == 15) { over_lane = j; over_s = sft; }
+                        else sft = v;
+                    }
+                }
+                const bool kept = active && (over_lane < 0 || lane < over_lane);
+                bool kept_mem = false;
+                if (kept) {
+                    const int out = (int)((table >> (4 * my_in)) & 15u);  // my accepted draw is k0 + out
+                    const int cand = ring[(qbase + (uint32_t)(k0 + out)) & (RDF_RING - 1)];
+                    kept_mem = (M >> out) & 1u;
+                    neg = (cand == item) ? -1 : cand;  // give-up case only: the draw may be the positive itself
+                }
+                int consumed;
+                if (over_lane < 0) {
+                    consumed = (nvalid - start) + sft;  // one kept draw per interaction + the rejected ones
+                    c_rej += (unsigned long long)sft;
+                    start = nvalid;
                 } else {
-                    const int fl = __ffs(R) - 1;
-                    f = __shfl_sync(LFM_FULL, rank, fl);
-                    consumed = f - start + 1;
-                    if (lane == fl) attempts = (rank == start ? attempts : 0) + 1;
-                    c_rej++;
+                    const int f = __shfl_sync(LFM_FULL, rank, over_lane);
+                    consumed = (f - start) + RDF_W;     // ... and the whole window of the lane that ran out
+                    c_rej += (unsigned long long)RDF_W;  // over_s by the lanes before it, W - over_s by itself
+                    if (lane == over_lane) attempts = (rank == start ? attempts : 0) + (RDF_W - over_s);
+                    start = f;
                 }
-                const bool kept = active && rank < f;
-                if (kept) neg = (cand == item) ? -1 : cand;  // give-up case only: the draw may be the positive itself
-                c_rej += __popc(__ballot_sync(LFM_FULL, kept && mem));  // replay_kernel counts a kept member draw too
+                c_rej += __popc(__ballot_sync(LFM_FULL, kept && kept_mem));  // replay_kernel counts a kept member draw too
                 c_neg += (unsigned long long)consumed;
-                start = f;
                 qbase += (uint32_t)consumed;
-                __syncwarp();  // every lane has read its candidate before the ring moves on
+                __syncwarp();  // every lane has read its candidates before the ring moves on
                 fetch(consumed);
             }
             if (valid && neg >= 0) en = cnt_item[neg];
@@ -533,7 +585,16 @@ static cudaError_t lfm_try_launch_replay_dataflow(int loss, const FitArgs& a, cu
         }
     }
     size_t smem = sizeof(float) * 3 * (d + 1) * RDF_WARPS;
-    if (s.cnt_in_smem && cnt_bytes > smem) smem = cnt_bytes;
+    size_t sched_smem = s.cnt_in_smem ? cnt_bytes : 0;
+    s.bitmap_in_smem = 0;
+    if (s.bitmap) {
+        const size_t bm = sizeof(uint32_t) * (size_t)s.bitmap_words * (size_t)a.pos.rows;
+        if (sched_smem + bm <= 216 * 1024) {
+            s.bitmap_in_smem = 1;
+            sched_smem += bm;
+        }
+    }
+    if (sched_smem > smem) smem = sched_smem;
     void* args[2] = {(void*)&a, (void*)&s};
     cudaEventRecord(g_rdf_ev[0], st);
 #define RDF_LAUNCH(L, KK, AA)                                                                              \

@@ -18,6 +18,8 @@
 //   warp_update T:537-649, regularize T:652-675, fit_logistic T:694-781,
 //   fit_warp T:784-912, fit_warp_kos T:915-1071, fit_bpr T:1074-1182.
 #include <atomic>
+#include <cstdio>
+#include <cstdlib>
 
 #include "lfm_common.cuh"
 

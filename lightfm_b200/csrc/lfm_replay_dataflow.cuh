@@ -44,6 +44,7 @@ struct RdfScratch {
     int32_t* cnt_item;  //                                       [n_items]
     int32_t* ver_user;  // executors: published row versions     [n_users]
     int32_t* ver_item;  //                                       [n_items]
+    int32_t* mark;      // scheduler (BPR): chunk marks            [2 * n_items] (global fallback)
     RdfTask* tasks;     // [n]
     const Tuple* tuples;  // [n] the interactions in visiting order (pack_kernel), user < 0: skipped
     const uint32_t* bitmap;  // optional exact membership bitmap of the positives CSR (else null)
@@ -96,15 +97,27 @@ __device__ __forceinline__ void rdf_schedule(const FitArgs& a, const RdfScratch&
         for (int i = lane; i < a.model.user.n + a.model.item.n; i += 32) cnt_smem[i] = 0;
         __syncwarp();
     }
+    // mark arrays of the BPR version step (item id -> last chunk that touched it as positive / negative)
+    int32_t* mark_pos = s.mark;
+    int32_t* mark_neg = s.mark + a.model.item.n;
+    if (LOSS == LOSS_BPR && s.cnt_in_smem) {
+        mark_pos = cnt_smem + a.model.user.n + a.model.item.n;
+        mark_neg = mark_pos + a.model.item.n;
+        for (int i = lane; i < 2 * a.model.item.n; i += 32) mark_pos[i] = 0;
+        __syncwarp();
+    }
     // membership bitmap: a copy in shared memory when the host found room for it
     const uint32_t* bitmap = s.bitmap;
     if (LOSS == LOSS_BPR && s.bitmap && s.bitmap_in_smem) {
-        uint32_t* sb = (uint32_t*)(cnt_smem + (s.cnt_in_smem ? a.model.user.n + a.model.item.n : 0));
+        uint32_t* sb = (uint32_t*)(cnt_smem + (s.cnt_in_smem ? a.model.user.n + 3 * a.model.item.n : 0));
         const int total = a.pos.rows * s.bitmap_words;
         for (int i = lane; i < total; i += 32) sb[i] = s.bitmap[i];
         __syncwarp();
         bitmap = sb;
     }
+    // draws judged per interaction per round: the whole window when a test is a shared-memory load,
+    // two when it is a random DRAM / L2 access, one when it is a binary search
+    const int wuse = (LOSS == LOSS_BPR && s.bitmap) ? (s.bitmap_in_smem ? RDF_W : 2) : 1;
     // LCG jump-ahead (rand_r's state update, T:76): lane l holds (A^(l+1), C_(l+1)) with
     // state after l+1 draws = A^(l+1) * state + C_(l+1)
     uint32_t ja = 1103515245u, jc = 12345u;
@@ -142,6 +155,7 @@ __device__ __forceinline__ void rdf_schedule(const FitArgs& a, const RdfScratch&
         for (int g = 0; g < RDF_AHEAD / 32; g++) fetch(32);
     unsigned long long c_neg = 0, c_rej = 0;
     int out_base = 0;
+    long long pf_load = 0, pf_sample = 0, pf_version = 0, pf_emit = 0, pf_rounds = 0;  // cycles per phase (profile)
 
     // tuple pipeline: the list was packed in visiting order by pack_kernel, so the scheduler streams
     // it (one 16 B tuple per lane per chunk), two chunks ahead in registers and RDF_PF chunks ahead in L2
@@ -155,6 +169,7 @@ __device__ __forceinline__ void rdf_schedule(const FitArgs& a, const RdfScratch&
     int4 tp1 = load_tuple(lane), tp2 = load_tuple(32 + lane);
     int chunk = 0;
     for (int64_t t0 = 0; t0 < n; t0 += 32, chunk++) {
+        const long long pc0 = clock64();
         const bool in = t0 + lane < n;
         const int user = tp1.x, item = tp1.y;
         const float w = __int_as_float(tp1.z), y = __int_as_float(tp1.w);
@@ -172,6 +187,7 @@ __device__ __forceinline__ void rdf_schedule(const FitArgs& a, const RdfScratch&
             ei = cnt_item[item];
         }
         int neg = -1;
+        const long long pc1 = clock64();
         if (LOSS == LOSS_BPR) {
             int ps = 0, pe = 0;
             const uint32_t* brow = nullptr;
@@ -191,48 +207,56 @@ __device__ __forceinline__ void rdf_schedule(const FitArgs& a, const RdfScratch&
             // its own rejections), and the shifts are then resolved lane after lane.  A chunk is done
             // in one round unless more than W - 1 rejections pile up before some lane.
             while (start < nvalid) {
+                pf_rounds++;
                 const bool active = valid && rank >= start;
                 const int k0 = active ? rank - start : 0;
                 rp_wait<RDF_WAIT>();  // the groups holding draws qbase .. qbase + 31 + W have landed
                 __syncwarp();
-                unsigned M = 0;  // bit j: draw k0 + j names one of my positives
+                unsigned M = 0;  // bit j: draw k0 + j names one of my positives (j < wuse)
                 if (active) {
+                    if (brow) {
+                        uint32_t word[RDF_W];
+                        int bit[RDF_W];
 #pragma unroll
-                    for (int j = 0; j < RDF_W; j++) {
-                        const int cand = ring[(qbase + (uint32_t)(k0 + j)) & (RDF_RING - 1)];
-                        bool mem;
-                        if (brow) mem = (brow[cand >> 5] >> (cand & 31)) & 1u;
-                        else mem = lfm_bsearch(a.pos.indices, ps, pe, cand);
-                        M |= (mem ? 1u : 0u) << j;
+                        for (int j = 0; j < RDF_W; j++) {  // all loads of the window in flight together
+                            const int cand = ring[(qbase + (uint32_t)(k0 + j)) & (RDF_RING - 1)];
+                            bit[j] = cand & 31;
+                            word[j] = j < wuse ? brow[cand >> 5] : 0u;
+                        }
+#pragma unroll
+                        for (int j = 0; j < RDF_W; j++) M |= ((word[j] >> bit[j]) & 1u) << j;
+                    } else {
+                        for (int j = 0; j < wuse; j++) {
+                            const int cand = ring[(qbase + (uint32_t)(k0 + j)) & (RDF_RING - 1)];
+                            M |= (lfm_bsearch(a.pos.indices, ps, pe, cand) ? 1u : 0u) << j;
+                        }
                     }
                 }
                 // T:1123-1127: the loop gives up after no_examples draws and keeps the last one, so a
                 // member draw is a rejection only while fewer than n - 1 draws were rejected before it
                 int64_t lim64 = n - 1 - ((rank == start) ? attempts : 0);
                 const int lim = lim64 > 64 ? 64 : (lim64 < 0 ? 0 : (int)lim64);
-                unsigned table = 0;  // 4 bits per incoming shift s: outgoing shift, 15 = beyond the window
-#pragma unroll
-                for (int sft = 0; sft < RDF_W; sft++) {
-                    const int run = __ffs(~(M >> sft)) - 1;  // consecutive member draws from draw k0 + sft
-                    const int rr = run < lim ? run : lim;
-                    table |= (unsigned)(sft + rr <= RDF_W - 1 ? sft + rr : 15) << (4 * sft);
-                }
+                // resolve the lanes in order: incoming shift -> my rejections -> outgoing shift
+                const unsigned packed = M | ((unsigned)lim << 8);
                 const unsigned A = __ballot_sync(LFM_FULL, active);
                 int sft = 0, my_in = 0, over_lane = -1, over_s = 0;
-#pragma unroll 4
+#pragma unroll 8
                 for (int j = 0; j < 32; j++) {
-                    const unsigned tj = __shfl_sync(LFM_FULL, table, j);
+                    const unsigned pj = __shfl_sync(LFM_FULL, packed, j);
                     if (((A >> j) & 1u) && over_lane < 0) {
                         if (j == lane) my_in = sft;
-                        const int v = (int)((tj >> (4 * sft)) & 15u);
-                        if (v == 15) { over_lane = j; over_s = sft; }
+                        const int run = __ffs(~((pj & 0xffu) >> sft)) - 1;  // consecutive member draws from draw k0 + sft
+                        const int lj = (int)(pj >> 8);
+                        const int v = sft + (run < lj ? run : lj);
+                        if (v > wuse - 1) { over_lane = j; over_s = sft; }
                         else sft = v;
                     }
                 }
                 const bool kept = active && (over_lane < 0 || lane < over_lane);
                 bool kept_mem = false;
                 if (kept) {
-                    const int out = (int)((table >> (4 * my_in)) & 15u);  // my accepted draw is k0 + out
+                    const int run = __ffs(~(M >> my_in)) - 1;
+                    const int out = my_in + (run < lim ? run : lim);  // my accepted draw is k0 + out
                     const int cand = ring[(qbase + (uint32_t)(k0 + out)) & (RDF_RING - 1)];
                     kept_mem = (M >> out) & 1u;
                     neg = (cand == item) ? -1 : cand;  // give-up case only: the draw may be the positive itself
@@ -244,9 +268,9 @@ __device__ __forceinline__ void rdf_schedule(const FitArgs& a, const RdfScratch&
                     start = nvalid;
                 } else {
                     const int f = __shfl_sync(LFM_FULL, rank, over_lane);
-                    consumed = (f - start) + RDF_W;     // ... and the whole window of the lane that ran out
-                    c_rej += (unsigned long long)RDF_W;  // over_s by the lanes before it, W - over_s by itself
-                    if (lane == over_lane) attempts = (rank == start ? attempts : 0) + (RDF_W - over_s);
+                    consumed = (f - start) + wuse;      // ... and the whole window of the lane that ran out
+                    c_rej += (unsigned long long)wuse;  // over_s by the lanes before it, wuse - over_s by itself
+                    if (lane == over_lane) attempts = (rank == start ? attempts : 0) + (wuse - over_s);
                     start = f;
                 }
                 c_rej += __popc(__ballot_sync(LFM_FULL, kept && kept_mem));  // replay_kernel counts a kept member draw too
@@ -258,6 +282,7 @@ __device__ __forceinline__ void rdf_schedule(const FitArgs& a, const RdfScratch&
             if (valid && neg >= 0) en = cnt_item[neg];
         }
         // versions: + touches by the lanes below me; and am I the last lane of the chunk on each row
+        const long long pc2 = clock64();
         bool lu = true, li = true, ln = true;
         {
             const unsigned gt = ~lt & ~(1u << lane);
@@ -271,21 +296,41 @@ __device__ __forceinline__ void rdf_schedule(const FitArgs& a, const RdfScratch&
             }
         }
         if (LOSS == LOSS_BPR) {
-#pragma unroll 4
-            for (int j = 0; j < 32; j++) {  // an item row is touched as a positive or as a negative
+            // an item row is touched as a positive or as a negative.  Same-kind touches: match.any.
+            // Cross touches (my positive = someone's negative or the reverse) are found through two
+            // mark arrays indexed by item id, and only the lanes involved in one are walked.
+            const unsigned gt = ~lt & ~(1u << lane);
+            const int cid = chunk + 1;
+            const unsigned mp = __match_any_sync(LFM_FULL, valid ? item : -1 - lane) & V;
+            const unsigned mn = __match_any_sync(LFM_FULL, (valid && neg >= 0) ? neg : -1 - lane) & V;
+            ei += __popc(mp & lt);
+            li = (mp & gt) == 0;
+            en += __popc(mn & lt);
+            ln = (mn & gt) == 0;
+            if (valid) {
+                mark_pos[item] = cid;
+                if (neg >= 0) mark_neg[neg] = cid;
+            }
+            __syncwarp();
+            const bool cross = valid && ((neg >= 0 && mark_pos[neg] == cid) || mark_neg[item] == cid);
+            unsigned C = __ballot_sync(LFM_FULL, cross);
+            while (C) {
+                const int j = __ffs(C) - 1;
+                C &= C - 1;
                 const int pj = __shfl_sync(LFM_FULL, item, j), nj = __shfl_sync(LFM_FULL, neg, j);
-                if (((V >> j) & 1u) && valid && j != lane) {
-                    const bool mi = pj == item || nj == item;
-                    const bool mn = neg >= 0 && (pj == neg || nj == neg);
+                if (valid && j != lane) {
+                    const bool x1 = nj == item;              // lane j's negative is my positive
+                    const bool x2 = neg >= 0 && pj == neg;   // lane j's positive is my negative
                     if (j < lane) {
-                        ei += mi; en += mn;
+                        ei += x1; en += x2;
                     } else {
-                        li = li && !mi; ln = ln && !mn;
+                        li = li && !x1; ln = ln && !x2;
                     }
                 }
             }
         }
         __syncwarp();  // every lane has read the counters before they move
+        const long long pc3 = clock64();
         if (valid) {
             // one store per row: the last lane on it writes the count after this chunk
             if (lu) cnt_user[user] = eu + 1;
@@ -300,6 +345,9 @@ __device__ __forceinline__ void rdf_schedule(const FitArgs& a, const RdfScratch&
         out_base += nvalid;
         __syncwarp();  // counters (same SM: shared memory / L1) and tasks written before the next chunk reads
         if ((chunk % RDF_PUBLISH) == RDF_PUBLISH - 1 && lane == 0) rdf_st_release(s.header + RDF_H_PRODUCED, out_base);
+        __syncwarp();
+        const long long pc4 = clock64();
+        pf_load += pc1 - pc0; pf_sample += pc2 - pc1; pf_version += pc3 - pc2; pf_emit += pc4 - pc3;
     }
     __syncwarp();
     if (lane == 0) {
@@ -311,6 +359,9 @@ __device__ __forceinline__ void rdf_schedule(const FitArgs& a, const RdfScratch&
         a.counters->rejected = c_rej;
         s.header[RDF_H_TOTAL] = out_base;
         s.header[RDF_H_SCHED_US] = (int32_t)((rdf_now_ns() - t_begin) / 1000ull);
+        s.header[8] = (int32_t)(pf_load >> 10); s.header[9] = (int32_t)(pf_sample >> 10);      // kilo-cycles
+        s.header[10] = (int32_t)(pf_version >> 10); s.header[11] = (int32_t)(pf_emit >> 10);
+        s.header[12] = (int32_t)pf_rounds; s.header[13] = chunk;
         rdf_st_release(s.header + RDF_H_PRODUCED, out_base);
         rdf_st_release(s.header + RDF_H_DONE, 1);
     }
@@ -518,7 +569,7 @@ static size_t rdf_scratch_bytes(int loss, const FitArgs& a, int64_t bitmap_limit
         a.user_alpha != 0.0 || m.d > 256 || m.d < 1 || a.n > 0x7fffffffLL || a.n < 1)
         return 0;
     if (loss == LOSS_BPR && !a.pos.indptr) return 0;
-    size_t b = 256 + sizeof(int32_t) * 2 * ((size_t)m.user.n + (size_t)m.item.n + 64) +
+    size_t b = 256 + sizeof(int32_t) * (2 * ((size_t)m.user.n + (size_t)m.item.n + 64) + 2 * (size_t)m.item.n) +
                (sizeof(RdfTask) + sizeof(Tuple)) * (size_t)a.n + 1024;
     if (loss == LOSS_BPR) {
         const size_t words = ((size_t)a.pos.cols + 31) / 32;
@@ -556,7 +607,9 @@ static cudaError_t lfm_try_launch_replay_dataflow(int loss, const FitArgs& a, cu
     s.cnt_item = s.cnt_user + nu;
     s.ver_user = s.cnt_item + ni;
     s.ver_item = s.ver_user + nu;
-    size_t off = 256 + sizeof(int32_t) * 2 * (nu + ni + 64);
+    s.mark = s.ver_item + ni;
+    const size_t zero_bytes = 256 + sizeof(int32_t) * (2 * (nu + ni + 64) + 2 * ni);
+    size_t off = zero_bytes;
     off = (off + 255) & ~(size_t)255;
     s.tasks = (RdfTask*)(base + off);
     off += sizeof(RdfTask) * (size_t)a.n;
@@ -568,9 +621,10 @@ static cudaError_t lfm_try_launch_replay_dataflow(int loss, const FitArgs& a, cu
     s.bitmap = nullptr;
     s.bitmap_words = 0;
     s.mod_magic = ~0ull / (uint64_t)a.n + 1ull;
-    const size_t cnt_bytes = sizeof(int32_t) * (nu + ni);
+    // scheduler state in shared memory: touch counters [nu + ni] and, for BPR, the two mark arrays [2 ni]
+    const size_t cnt_bytes = sizeof(int32_t) * (nu + ni + (loss == LOSS_BPR ? 2 * ni : 0));
     s.cnt_in_smem = cnt_bytes <= 160 * 1024 ? 1 : 0;
-    cudaError_t e = cudaMemsetAsync(base, 0, 256 + sizeof(int32_t) * 2 * (nu + ni + 64), st);
+    cudaError_t e = cudaMemsetAsync(base, 0, zero_bytes, st);
     if (e != cudaSuccess) return e;
     e = lfm_launch_pack(a, loss, tuples, 0u, st);  // the host shuffle order (a.shuffle), Y <= 0 marked for BPR
     if (e != cudaSuccess) return e;
@@ -589,7 +643,7 @@ static cudaError_t lfm_try_launch_replay_dataflow(int loss, const FitArgs& a, cu
     s.bitmap_in_smem = 0;
     if (s.bitmap) {
         const size_t bm = sizeof(uint32_t) * (size_t)s.bitmap_words * (size_t)a.pos.rows;
-        if (sched_smem + bm <= 216 * 1024) {
+        if (sched_smem + bm <= 226 * 1024) {  // 227 KB per CTA minus the scheduler's static ring
             s.bitmap_in_smem = 1;
             sched_smem += bm;
         }
@@ -610,6 +664,7 @@ static cudaError_t lfm_try_launch_replay_dataflow(int loss, const FitArgs& a, cu
         if (per_sm < 1) return cudaErrorNotSupported;                                                      \
         /* one CTA per SM: ~1200 warps, far more than the graph is wide; CTA 0 = the scheduler */          \
         int64_t blocks = sms;                                                                              \
+        if (const char* ev = getenv("LFM_RDF_CTAS")) { const int v = atoi(ev); if (v >= 2 && v <= sms) blocks = v; } \
         const int64_t need = 1 + (a.n + RDF_WARPS - 1) / RDF_WARPS;                                        \
         if (blocks > need) blocks = need;                                                                  \
         e = cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)blocks), dim3(RDF_WARPS * 32), args, \
@@ -633,7 +688,7 @@ static cudaError_t lfm_try_launch_replay_dataflow(int loss, const FitArgs& a, cu
 #undef RDF_LAUNCH
     if (e != cudaSuccess) return e;
     cudaEventRecord(g_rdf_ev[1], st);
-    int32_t hdr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int32_t hdr[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     e = cudaMemcpyAsync(hdr, s.header, sizeof(hdr), cudaMemcpyDeviceToHost, st);
     if (e != cudaSuccess) return e;
     e = cudaStreamSynchronize(st);
@@ -644,5 +699,9 @@ static cudaError_t lfm_try_launch_replay_dataflow(int loss, const FitArgs& a, cu
     g_rdf_ms[0] = hdr[RDF_H_SCHED_US] / 1000.0;
     g_rdf_ms[1] = ms;
     g_rdf_tasks = hdr[RDF_H_TOTAL];
+    if (getenv("LFM_RDF_PROFILE"))
+        fprintf(stderr, "[rdf] tasks %d kernel %.3f ms scheduler %.3f ms | scheduler kcycles: load %d sample %d version %d emit %d | "
+                        "rounds %d chunks %d | smem cnt %d bitmap %d\n", hdr[RDF_H_TOTAL], ms, hdr[RDF_H_SCHED_US] / 1000.0,
+                hdr[8], hdr[9], hdr[10], hdr[11], hdr[12], hdr[13], s.cnt_in_smem, s.bitmap_in_smem);
     return cudaSuccess;
 }

@@ -34,3 +34,16 @@ def test_clock_sampler_parses_nvidia_smi_rows(tmp_path):
     assert out["samples"] == 2 and out["sm_max_mhz"] == 1965.0
     assert out["sm_mhz"] == (1965.0 + 1950.0) / 2
     assert out["reasons"] == ["sw_power_cap"]
+
+
+def test_ncu_dram_csv_parser():
+    import bench
+    text = ('"ID","Process ID","Process Name","Host Name","Kernel Name","Context","Stream","Block Size","Grid Size",'
+            '"Device","CC","Section Name","Metric Name","Metric Unit","Metric Value"\n'
+            '"0","1","python","h","fast_slot_kernel","1","7","(256, 1, 1)","(444, 1, 1)","0","10.0","Command line profiler metrics",'
+            '"dram__bytes_read.sum","Gbyte","6.12"\n'
+            '"0","1","python","h","fast_slot_kernel","1","7","(256, 1, 1)","(444, 1, 1)","0","10.0","Command line profiler metrics",'
+            '"dram__bytes_write.sum","Mbyte","3,499.5"\n')
+    total, seen = bench.parse_ncu_dram_csv(text)
+    assert seen == 2 and abs(total - (6.12e9 + 3499.5e6)) < 1.0
+    assert bench.parse_ncu_dram_csv("==PROF== nothing\n") == (0.0, 0)

@@ -542,15 +542,21 @@ __global__ void __launch_bounds__(256, MINB) fast_slot_kernel(FitArgs a, const T
                 float ba = 0.0f, bb = 0.0f;
 #pragma unroll
                 for (int v = 0; v < VPL; v++) qb[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                // the membership words of both candidates leave with their rows (they depend on the draw
+                // and the user only): a violating candidate then needs no further round trip
+                uint32_t wa = 0u, wb = 0u;
+                const uint32_t* brow = BITMAP ? a.pos_bitmap + (size_t)cur.user * a.bitmap_words : nullptr;
                 if (active) {
 #pragma unroll
                     for (int v = 0; v < VPL; v++) q[v] = ldcg4(m.item.w + (size_t)ca * D + (sub + LPR * v) * 4);
                     ba = __ldcg(m.item.b + ca);
+                    if (BITMAP) wa = __ldg(brow + (ca >> 5));
                 }
                 if (act_b) {
 #pragma unroll
                     for (int v = 0; v < VPL; v++) qb[v] = ldcg4(m.item.w + (size_t)cb * D + (sub + LPR * v) * 4);
                     bb = __ldcg(m.item.b + cb);
+                    if (BITMAP) wb = __ldg(brow + (cb >> 5));
                 }
                 float pa = 0.0f, pb2 = 0.0f;
 #pragma unroll
@@ -560,8 +566,6 @@ __global__ void __launch_bounds__(256, MINB) fast_slot_kernel(FitArgs a, const T
                 const bool va = active && npa > pp - 1.0f, vb = act_b && npb > pp - 1.0f;
                 bool ma, mb;
                 if (BITMAP) {
-                    const uint32_t* brow = a.pos_bitmap + (size_t)cur.user * a.bitmap_words;
-                    const uint32_t wa = va ? __ldg(brow + (ca >> 5)) : 0u, wb = vb ? __ldg(brow + (cb >> 5)) : 0u;
                     ma = va && ((wa >> (ca & 31)) & 1u);
                     mb = vb && ((wb >> (cb & 31)) & 1u);
                 } else {
@@ -601,10 +605,12 @@ __global__ void __launch_bounds__(256, MINB) fast_slot_kernel(FitArgs a, const T
                 const uint32_t r = w == 0 ? r4.x : w == 1 ? r4.y : w == 2 ? r4.z : r4.w;
                 const int cand = PROBE ? lfm_rand_r(rr_state) % n_items : lfm_bounded(r, (uint32_t)n_items);
                 float qb = 0.0f;
+                uint32_t wm = 0u;  // the candidate's membership word leaves with its row
                 if (active) {
 #pragma unroll
                     for (int v = 0; v < VPL; v++) q[v] = ldcg4(m.item.w + (size_t)cand * D + (sub + LPR * v) * 4);
                     qb = __ldcg(m.item.b + cand);
+                    if (BITMAP) wm = __ldg(a.pos_bitmap + (size_t)cur.user * a.bitmap_words + (cand >> 5));
                 }
                 float part = 0.0f;
 #pragma unroll
@@ -613,7 +619,7 @@ __global__ void __launch_bounds__(256, MINB) fast_slot_kernel(FitArgs a, const T
                 const bool viol = active && np > pp - 1.0f;
                 bool member;
                 if (BITMAP) {  // exact bitmap of the positives: one 4 B load instead of a search
-                    member = viol && ((__ldg(a.pos_bitmap + (size_t)cur.user * a.bitmap_words + (cand >> 5)) >> (cand & 31)) & 1u);
+                    member = viol && ((wm >> (cand & 31)) & 1u);
                 } else {
                     member = slot_member<LPR>(a.pos.indices, cs.ps, cs.pe, cs.probe, cand, viol, sub, slotmask);
                 }
@@ -636,6 +642,7 @@ __global__ void __launch_bounds__(256, MINB) fast_slot_kernel(FitArgs a, const T
             //      not one of the user's positives (almost always the first try) ----
             Philox4 r4 = {0u, 0u, 0u, 0u};
             bool active = valid;
+            float qb = 0.0f;
             for (int round = 0; __any_sync(LFM_FULL, active); round++) {
                 if ((round & 3) == 0)
                     r4 = philox7((uint32_t)t, 0u, (uint32_t)(round >> 2), 2u, a.seed, 0x4c464d31u);
@@ -646,7 +653,16 @@ __global__ void __launch_bounds__(256, MINB) fast_slot_kernel(FitArgs a, const T
                 const int cand = active ? __ldg(a.item_ids + j) : 0;
                 bool member;
                 if (BITMAP) {
-                    member = active && ((__ldg(a.pos_bitmap + (size_t)cur.user * a.bitmap_words + (cand >> 5)) >> (cand & 31)) & 1u);
+                    // the candidate's row leaves together with its membership word: the draw is almost
+                    // always kept, and then nothing is left to fetch
+                    uint32_t wm = 0u;
+                    if (active) {
+                        wm = __ldg(a.pos_bitmap + (size_t)cur.user * a.bitmap_words + (cand >> 5));
+#pragma unroll
+                        for (int v = 0; v < VPL; v++) q[v] = ldcg4(m.item.w + (size_t)cand * D + (sub + LPR * v) * 4);
+                        qb = __ldcg(m.item.b + cand);
+                    }
+                    member = active && ((wm >> (cand & 31)) & 1u);
                 } else {
                     member = slot_member<LPR>(a.pos.indices, cs.ps, cs.pe, cs.probe, cand, active, sub, slotmask);
                 }
@@ -657,8 +673,7 @@ __global__ void __launch_bounds__(256, MINB) fast_slot_kernel(FitArgs a, const T
                     active = member && sampled < 256;
                 }
             }
-            float qb = 0.0f;
-            if (valid) {
+            if (!BITMAP && valid) {
 #pragma unroll
                 for (int v = 0; v < VPL; v++) q[v] = ldcg4(m.item.w + (size_t)neg_id * D + (sub + LPR * v) * 4);
                 qb = __ldcg(m.item.b + neg_id);

@@ -12,11 +12,13 @@
 // interactions that share no row commute exactly (they read and write disjoint addresses).
 //
 // One cooperative kernel (rdf_kernel), two roles:
-//   * the SCHEDULER (one warp with an SM to itself) walks the shuffled list in order.  It consumes
-//     the rand_r stream exactly as the reference does (32 draws judged per round -- the state of
-//     draw k is an LCG jump-ahead, the candidates' item ids stream in ahead of time through a
-//     cp.async ring, a rejected draw re-aligns the round) and emits one task per interaction:
-//     {user, item, negative, versions}, `version` of a row = how many earlier interactions touch it;
+//   * the SCHEDULER (three warps of CTA 0, which has an SM to itself, pipelined over chunks of 32
+//     interactions) walks the shuffled list in order.  Stage S consumes the rand_r stream exactly as
+//     the reference does (the state of draw k is an LCG jump-ahead, the candidates' item ids stream
+//     in ahead of time through a cp.async ring, several draws are judged per interaction per round
+//     and the lanes resolved in order); stage V counts, for every row an interaction touches, how
+//     many earlier interactions touch it (its `version`); stage E emits one task per interaction:
+//     {user, item, negative, versions};
 //   * the EXECUTORS (every other SM, one warp per task, tasks handed out in visiting order) wait
 //     until the task exists and its rows have reached their versions, run the reference's
 //     arithmetic on them and publish version + 1 (st.release).  The earliest unfinished task never
@@ -60,7 +62,7 @@ struct RdfScratch {
 #define RDF_W 8          // draws judged per interaction per round
 #define RDF_WAIT 4       // cp.async groups that may still be in flight when a round reads the ring:
                          // a round consumes <= 32 + W draws and reads < qbase + 32 + W, (RDF_WAIT + 1) * 40 <= RDF_AHEAD
-#define RDF_PUBLISH 4    // the scheduler publishes its progress every RDF_PUBLISH chunks of 32
+#define RDF_PUBLISH 8    // the scheduler publishes its progress every RDF_PUBLISH chunks of 32
 #define RDF_PF 16         // chunks of the packed list prefetched into L2 ahead of the scheduler
 
 __device__ __forceinline__ int rdf_ld_acquire(const int32_t* p) {
@@ -82,38 +84,53 @@ __device__ __forceinline__ unsigned long long rdf_now_ns() {
     return t;
 }
 
-// ---- scheduler (one warp) ------------------------------------------------------------------
+// ---- scheduler: three warps of CTA 0 in a pipeline -------------------------------------------
+// S (sample): streams the packed list, gives every BPR interaction its negative (rand_r replay).
+// V (version): counts the earlier touches of every row an interaction touches.
+// E (emit): writes the tasks and publishes the scheduler's progress to the executors.
+// The stages hand chunks of 32 interactions to each other through two small shared-memory rings;
+// each stage is sequential in itself (that is what makes the result the reference's), but the
+// three run concurrently on different chunks.
+#define RDF_PIPE 3  // chunks a ring holds
+struct RdfChunkA {  // S -> V
+    int32_t user[32], item[32], neg[32];
+    float w[32], y[32];
+};
+struct RdfChunkB {  // V -> E
+    int32_t user[32], item[32], neg[32], eu[32], ei[32], en[32];
+    float w[32], y[32];
+};
+struct RdfPipe {
+    RdfChunkA a[RDF_PIPE];
+    RdfChunkB b[RDF_PIPE];
+    int32_t ring[RDF_RING];          // candidate ring of stage S
+    volatile int32_t a_prod, a_cons, b_prod, b_cons;  // chunk counters of the two rings
+};
+
+__device__ __forceinline__ void rdf_wait_ge(volatile int32_t* flag, int v, long long& waited) {
+    const long long t0 = clock64();
+    if (threadIdx.x % 32 == 0)
+        while (*flag < v) __nanosleep(64);
+    __threadfence_block();  // what the other stage wrote before the flag is read after it
+    __syncwarp();
+    waited += clock64() - t0;
+}
+
 template <int LOSS>
-__device__ __forceinline__ void rdf_schedule(const FitArgs& a, const RdfScratch& s, int32_t* cnt_smem) {
-    const int lane = threadIdx.x;
+__device__ __forceinline__ void rdf_stage_sample(const FitArgs& a, const RdfScratch& s, RdfPipe* pp, uint32_t* bitmap_smem) {
+    const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const int64_t n = a.n;
-    const unsigned long long t_begin = rdf_now_ns();
-    int32_t* cnt_user = s.cnt_user;
-    int32_t* cnt_item = s.cnt_item;
-    if (s.cnt_in_smem) {
-        cnt_user = cnt_smem;
-        cnt_item = cnt_smem + a.model.user.n;
-        for (int i = lane; i < a.model.user.n + a.model.item.n; i += 32) cnt_smem[i] = 0;
-        __syncwarp();
-    }
-    // mark arrays of the BPR version step (item id -> last chunk that touched it as positive / negative)
-    int32_t* mark_pos = s.mark;
-    int32_t* mark_neg = s.mark + a.model.item.n;
-    if (LOSS == LOSS_BPR && s.cnt_in_smem) {
-        mark_pos = cnt_smem + a.model.user.n + a.model.item.n;
-        mark_neg = mark_pos + a.model.item.n;
-        for (int i = lane; i < 2 * a.model.item.n; i += 32) mark_pos[i] = 0;
-        __syncwarp();
-    }
+    int32_t* ring = pp->ring;
+    long long waited = 0;
+    const long long t_begin = clock64();
     // membership bitmap: a copy in shared memory when the host found room for it
     const uint32_t* bitmap = s.bitmap;
     if (LOSS == LOSS_BPR && s.bitmap && s.bitmap_in_smem) {
-        uint32_t* sb = (uint32_t*)(cnt_smem + (s.cnt_in_smem ? a.model.user.n + 3 * a.model.item.n : 0));
         const int total = a.pos.rows * s.bitmap_words;
-        for (int i = lane; i < total; i += 32) sb[i] = s.bitmap[i];
+        for (int i = lane; i < total; i += 32) bitmap_smem[i] = s.bitmap[i];
         __syncwarp();
-        bitmap = sb;
+        bitmap = bitmap_smem;
     }
     // draws judged per interaction per round: the whole window when a test is a shared-memory load,
     // two when it is a random DRAM / L2 access, one when it is a binary search
@@ -133,7 +150,6 @@ __device__ __forceinline__ void rdf_schedule(const FitArgs& a, const RdfScratch&
     // Candidate ring (BPR): which item a draw names does not depend on who consumes it, so the
     // item_ids loads of the next RDF_AHEAD draws are always in flight (cp.async into shared memory)
     // and only the membership test of a round is a dependent load.
-    __shared__ int ring[RDF_RING];
     uint32_t fbase = a.seed;     // rand_r state before draw number `filled`
     uint32_t filled = 0, qbase = 0;
     auto fetch = [&](int count) {  // request the candidates of draws filled .. filled + count - 1 (count <= 64): one group
@@ -154,11 +170,10 @@ __device__ __forceinline__ void rdf_schedule(const FitArgs& a, const RdfScratch&
     if (LOSS == LOSS_BPR && n > 0)
         for (int g = 0; g < RDF_AHEAD / 32; g++) fetch(32);
     unsigned long long c_neg = 0, c_rej = 0;
-    int out_base = 0;
-    long long pf_load = 0, pf_sample = 0, pf_version = 0, pf_emit = 0, pf_rounds = 0;  // cycles per phase (profile)
+    long long rounds = 0;
 
     // tuple pipeline: the list was packed in visiting order by pack_kernel, so the scheduler streams
-    // it (one 16 B tuple per lane per chunk), two chunks ahead in registers and RDF_PF chunks ahead in L2
+    // it (one 16 B tuple per lane per chunk), three chunks ahead in registers and RDF_PF chunks ahead in L2
     const int4* tup = (const int4*)s.tuples;
     auto load_tuple = [&](int64_t t) -> int4 { return t < n ? __ldcg(tup + t) : make_int4(-1, 0, 0, 0); };
     auto prefetch = [&](int64_t t) {
@@ -166,28 +181,20 @@ __device__ __forceinline__ void rdf_schedule(const FitArgs& a, const RdfScratch&
     };
 #pragma unroll 1
     for (int c = 0; c < RDF_PF; c++) prefetch((int64_t)c * 32 + lane);
-    int4 tp1 = load_tuple(lane), tp2 = load_tuple(32 + lane);
+    int4 tp1 = load_tuple(lane), tp2 = load_tuple(32 + lane), tp3 = load_tuple(64 + lane);
     int chunk = 0;
     for (int64_t t0 = 0; t0 < n; t0 += 32, chunk++) {
-        const long long pc0 = clock64();
-        const bool in = t0 + lane < n;
         const int user = tp1.x, item = tp1.y;
-        const float w = __int_as_float(tp1.z), y = __int_as_float(tp1.w);
+        const int wbits = tp1.z, ybits = tp1.w;
         tp1 = tp2;
-        tp2 = load_tuple(t0 + 64 + lane);
+        tp2 = tp3;
+        tp3 = load_tuple(t0 + 96 + lane);
         prefetch(t0 + (int64_t)RDF_PF * 32 + lane);
-        const bool valid = in && user >= 0;  // pack_kernel marks BPR's Y <= 0 interactions (T:1112-1113) with user = -1
+        const bool valid = user >= 0;  // beyond the list, or one of BPR's Y <= 0 interactions (T:1112-1113: pack_kernel marks them)
         const unsigned V = __ballot_sync(LFM_FULL, valid);
         const int nvalid = __popc(V);
         const int rank = __popc(V & lt);
-        // touch counters of my rows as the earlier chunks left them (independent of the sampling below)
-        int eu = 0, ei = 0, en = 0;
-        if (valid) {
-            eu = cnt_user[user];
-            ei = cnt_item[item];
-        }
         int neg = -1;
-        const long long pc1 = clock64();
         if (LOSS == LOSS_BPR) {
             int ps = 0, pe = 0;
             const uint32_t* brow = nullptr;
@@ -201,13 +208,13 @@ __device__ __forceinline__ void rdf_schedule(const FitArgs& a, const RdfScratch&
             }
             int start = 0;     // valid interactions of this chunk already given their negative
             int attempts = 0;  // draws the interaction at rank == start has already rejected
-            // One round judges RDF_W consecutive draws per interaction: lane r (counted from `start`)
-            // would take draw r if nobody before it rejected anything, draw r + s after s rejections.
-            // Its membership bits for draws r .. r + W - 1 give f_r(s) = the shift it passes on (s plus
-            // its own rejections), and the shifts are then resolved lane after lane.  A chunk is done
-            // in one round unless more than W - 1 rejections pile up before some lane.
+            // One round judges `wuse` consecutive draws per interaction: lane r (counted from `start`)
+            // would take draw r if nobody before it rejected anything, draw r + s after s rejections;
+            // its membership bits for draws r .. r + wuse - 1 turn an incoming shift into an outgoing
+            // one, and the lanes are resolved in order.  A chunk is done in one round unless more than
+            // wuse - 1 rejections pile up before some lane.
             while (start < nvalid) {
-                pf_rounds++;
+                rounds++;
                 const bool active = valid && rank >= start;
                 const int k0 = active ? rank - start : 0;
                 rp_wait<RDF_WAIT>();  // the groups holding draws qbase .. qbase + 31 + W have landed
@@ -279,10 +286,65 @@ __device__ __forceinline__ void rdf_schedule(const FitArgs& a, const RdfScratch&
                 __syncwarp();  // every lane has read its candidates before the ring moves on
                 fetch(consumed);
             }
-            if (valid && neg >= 0) en = cnt_item[neg];
+        }
+        // hand the chunk to stage V
+        rdf_wait_ge(&pp->a_cons, chunk - (RDF_PIPE - 1), waited);
+        RdfChunkA& o = pp->a[chunk % RDF_PIPE];
+        o.user[lane] = user; o.item[lane] = item; o.neg[lane] = neg;
+        o.w[lane] = __int_as_float(wbits); o.y[lane] = __int_as_float(ybits);
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) pp->a_prod = chunk + 1;
+    }
+    if (lane == 0) {
+        a.counters->negatives = c_neg;
+        a.counters->rejected = c_rej;
+        s.header[8] = (int32_t)((clock64() - t_begin - waited) >> 10);  // kilo-cycles of work
+        s.header[9] = (int32_t)(waited >> 10);
+        s.header[14] = (int32_t)rounds;
+    }
+}
+
+template <int LOSS>
+__device__ __forceinline__ void rdf_stage_version(const FitArgs& a, const RdfScratch& s, RdfPipe* pp, int32_t* cnt_smem) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int nchunks = (int)((a.n + 31) / 32);
+    long long waited = 0;
+    const long long t_begin = clock64();
+    int32_t* cnt_user = s.cnt_user;
+    int32_t* cnt_item = s.cnt_item;
+    // mark arrays of the BPR version step (item id -> last chunk that touched it as positive / negative)
+    int32_t* mark_pos = s.mark;
+    int32_t* mark_neg = s.mark + a.model.item.n;
+    if (s.cnt_in_smem) {
+        cnt_user = cnt_smem;
+        cnt_item = cnt_smem + a.model.user.n;
+        const int total = a.model.user.n + a.model.item.n + (LOSS == LOSS_BPR ? 2 * a.model.item.n : 0);
+        for (int i = lane; i < total; i += 32) cnt_smem[i] = 0;
+        if (LOSS == LOSS_BPR) {
+            mark_pos = cnt_smem + a.model.user.n + a.model.item.n;
+            mark_neg = mark_pos + a.model.item.n;
+        }
+        __syncwarp();
+    }
+    for (int chunk = 0; chunk < nchunks; chunk++) {
+        rdf_wait_ge(&pp->a_prod, chunk + 1, waited);
+        const RdfChunkA& in = pp->a[chunk % RDF_PIPE];
+        const int user = in.user[lane], item = in.item[lane], neg = in.neg[lane];
+        const float w = in.w[lane], y = in.y[lane];
+        __syncwarp();
+        if (lane == 0) pp->a_cons = chunk + 1;
+        const bool valid = user >= 0;
+        const unsigned V = __ballot_sync(LFM_FULL, valid);
+        // touch counters of my rows as the earlier chunks left them
+        int eu = 0, ei = 0, en = 0;
+        if (valid) {
+            eu = cnt_user[user];
+            ei = cnt_item[item];
+            if (LOSS == LOSS_BPR && neg >= 0) en = cnt_item[neg];
         }
         // versions: + touches by the lanes below me; and am I the last lane of the chunk on each row
-        const long long pc2 = clock64();
         bool lu = true, li = true, ln = true;
         {
             const unsigned gt = ~lt & ~(1u << lane);
@@ -330,38 +392,63 @@ __device__ __forceinline__ void rdf_schedule(const FitArgs& a, const RdfScratch&
             }
         }
         __syncwarp();  // every lane has read the counters before they move
-        const long long pc3 = clock64();
         if (valid) {
             // one store per row: the last lane on it writes the count after this chunk
             if (lu) cnt_user[user] = eu + 1;
             if (li) cnt_item[item] = ei + 1;
             if (LOSS == LOSS_BPR && neg >= 0 && ln) cnt_item[neg] = en + 1;
-            RdfTask tk;
-            tk.user = user; tk.item = item; tk.neg = neg;
-            tk.eu = eu; tk.ei = ei; tk.en = en;
-            tk.weight = w; tk.y = y;
-            s.tasks[out_base + rank] = tk;
         }
-        out_base += nvalid;
-        __syncwarp();  // counters (same SM: shared memory / L1) and tasks written before the next chunk reads
-        if ((chunk % RDF_PUBLISH) == RDF_PUBLISH - 1 && lane == 0) rdf_st_release(s.header + RDF_H_PRODUCED, out_base);
+        // hand the chunk to stage E
+        rdf_wait_ge(&pp->b_cons, chunk - (RDF_PIPE - 1), waited);
+        RdfChunkB& o = pp->b[chunk % RDF_PIPE];
+        o.user[lane] = user; o.item[lane] = item; o.neg[lane] = neg;
+        o.eu[lane] = eu; o.ei[lane] = ei; o.en[lane] = en;
+        o.w[lane] = w; o.y[lane] = y;
+        __threadfence_block();
+        __syncwarp();  // also: counters (same SM: shared memory / L1) written before the next chunk reads them
+        if (lane == 0) pp->b_prod = chunk + 1;
+    }
+    if (lane == 0) {
+        s.header[10] = (int32_t)((clock64() - t_begin - waited) >> 10);
+        s.header[11] = (int32_t)(waited >> 10);
+    }
+}
+
+__device__ __forceinline__ void rdf_stage_emit(const FitArgs& a, const RdfScratch& s, RdfPipe* pp) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int nchunks = (int)((a.n + 31) / 32);
+    long long waited = 0;
+    const long long t_begin = clock64();
+    const unsigned long long ns_begin = rdf_now_ns();
+    int out_base = 0;
+    for (int chunk = 0; chunk < nchunks; chunk++) {
+        rdf_wait_ge(&pp->b_prod, chunk + 1, waited);
+        const RdfChunkB& in = pp->b[chunk % RDF_PIPE];
+        RdfTask tk;
+        tk.user = in.user[lane]; tk.item = in.item[lane]; tk.neg = in.neg[lane];
+        tk.eu = in.eu[lane]; tk.ei = in.ei[lane]; tk.en = in.en[lane];
+        tk.weight = in.w[lane]; tk.y = in.y[lane];
         __syncwarp();
-        const long long pc4 = clock64();
-        pf_load += pc1 - pc0; pf_sample += pc2 - pc1; pf_version += pc3 - pc2; pf_emit += pc4 - pc3;
+        if (lane == 0) pp->b_cons = chunk + 1;
+        const bool valid = tk.user >= 0;
+        const unsigned V = __ballot_sync(LFM_FULL, valid);
+        if (valid) s.tasks[out_base + __popc(V & lt)] = tk;
+        out_base += __popc(V);
+        __syncwarp();
+        if ((chunk % RDF_PUBLISH) == RDF_PUBLISH - 1 && lane == 0) rdf_st_release(s.header + RDF_H_PRODUCED, out_base);
     }
     __syncwarp();
     if (lane == 0) {
         a.scales->item_scale = 1.0;  // alpha == 0: the scales never leave 1
         a.scales->user_scale = 1.0;
         a.counters->positives = (unsigned long long)out_base;
-        a.counters->negatives = c_neg;
         a.counters->updates = (unsigned long long)out_base;
-        a.counters->rejected = c_rej;
         s.header[RDF_H_TOTAL] = out_base;
-        s.header[RDF_H_SCHED_US] = (int32_t)((rdf_now_ns() - t_begin) / 1000ull);
-        s.header[8] = (int32_t)(pf_load >> 10); s.header[9] = (int32_t)(pf_sample >> 10);      // kilo-cycles
-        s.header[10] = (int32_t)(pf_version >> 10); s.header[11] = (int32_t)(pf_emit >> 10);
-        s.header[12] = (int32_t)pf_rounds; s.header[13] = chunk;
+        s.header[RDF_H_SCHED_US] = (int32_t)((rdf_now_ns() - ns_begin) / 1000ull);
+        s.header[12] = (int32_t)((clock64() - t_begin - waited) >> 10);
+        s.header[13] = (int32_t)(waited >> 10);
+        s.header[15] = nchunks;
         rdf_st_release(s.header + RDF_H_PRODUCED, out_base);
         rdf_st_release(s.header + RDF_H_DONE, 1);
     }
@@ -447,6 +534,7 @@ __device__ __forceinline__ void rdf_execute(const FitArgs& a, const RdfScratch& 
                     __nanosleep(ahead > 200 ? 4000 : 100 + 20 * ahead);
                 }
             }
+            __syncwarp();  // lane 0's acquire is ordered before every lane's task load
             go = __shfl_sync(LFM_FULL, go, 0);
             produced = __shfl_sync(LFM_FULL, produced, 0);
             if (!go) return;
@@ -551,7 +639,19 @@ template <int LOSS, int K, int AD>
 __global__ void __launch_bounds__(RDF_WARPS * 32) rdf_kernel(FitArgs a, RdfScratch s) {
     extern __shared__ __align__(16) float rdf_smem[];
     if (blockIdx.x == 0) {
-        if (threadIdx.x < 32) rdf_schedule<LOSS>(a, s, (int32_t*)rdf_smem);
+        // scheduler state in shared memory: [touch counters + marks | bitmap copy | pipe]
+        int32_t* cnt_smem = (int32_t*)rdf_smem;
+        size_t off = s.cnt_in_smem ? (size_t)(a.model.user.n + a.model.item.n + (LOSS == LOSS_BPR ? 2 * a.model.item.n : 0)) : 0;
+        uint32_t* bitmap_smem = (uint32_t*)(cnt_smem + off);
+        if (LOSS == LOSS_BPR && s.bitmap_in_smem) off += (size_t)a.pos.rows * s.bitmap_words;
+        off = (off + 3) & ~(size_t)3;
+        RdfPipe* pp = (RdfPipe*)(cnt_smem + off);
+        if (threadIdx.x == 0) { pp->a_prod = 0; pp->a_cons = 0; pp->b_prod = 0; pp->b_cons = 0; }
+        __syncthreads();
+        const int w = threadIdx.x >> 5;
+        if (w == 0) rdf_stage_sample<LOSS>(a, s, pp, bitmap_smem);
+        else if (w == 1) rdf_stage_version<LOSS>(a, s, pp, cnt_smem);
+        else if (w == 2) rdf_stage_emit(a, s, pp);
         return;
     }
     // consecutive tasks go to different SMs: the runnable ones are always the earliest ones
@@ -641,13 +741,15 @@ static cudaError_t lfm_try_launch_replay_dataflow(int loss, const FitArgs& a, cu
     size_t smem = sizeof(float) * 3 * (d + 1) * RDF_WARPS;
     size_t sched_smem = s.cnt_in_smem ? cnt_bytes : 0;
     s.bitmap_in_smem = 0;
+    const size_t pipe_bytes = sizeof(RdfPipe) + 32;
     if (s.bitmap) {
         const size_t bm = sizeof(uint32_t) * (size_t)s.bitmap_words * (size_t)a.pos.rows;
-        if (sched_smem + bm <= 226 * 1024) {  // 227 KB per CTA minus the scheduler's static ring
+        if (sched_smem + bm + pipe_bytes <= 227 * 1024) {  // the per-CTA shared-memory limit of sm_100
             s.bitmap_in_smem = 1;
             sched_smem += bm;
         }
     }
+    sched_smem += pipe_bytes;
     if (sched_smem > smem) smem = sched_smem;
     void* args[2] = {(void*)&a, (void*)&s};
     cudaEventRecord(g_rdf_ev[0], st);
@@ -700,8 +802,8 @@ static cudaError_t lfm_try_launch_replay_dataflow(int loss, const FitArgs& a, cu
     g_rdf_ms[1] = ms;
     g_rdf_tasks = hdr[RDF_H_TOTAL];
     if (getenv("LFM_RDF_PROFILE"))
-        fprintf(stderr, "[rdf] tasks %d kernel %.3f ms scheduler %.3f ms | scheduler kcycles: load %d sample %d version %d emit %d | "
+        fprintf(stderr, "[rdf] tasks %d kernel %.3f ms scheduler %.3f ms | stage kcycles work/wait: sample %d/%d version %d/%d emit %d/%d | "
                         "rounds %d chunks %d | smem cnt %d bitmap %d\n", hdr[RDF_H_TOTAL], ms, hdr[RDF_H_SCHED_US] / 1000.0,
-                hdr[8], hdr[9], hdr[10], hdr[11], hdr[12], hdr[13], s.cnt_in_smem, s.bitmap_in_smem);
+                hdr[8], hdr[9], hdr[10], hdr[11], hdr[12], hdr[13], hdr[14], hdr[15], s.cnt_in_smem, s.bitmap_in_smem);
     return cudaSuccess;
 }

@@ -281,6 +281,10 @@ int lfm_plan_download(lfm_plan *plan, lfm_model *model);
 /* Refresh the resident state arrays and scalar hyper-parameters from `model` (shapes must equal
  * the plan's); interactions, features and the positives lookup stay as uploaded. */
 int lfm_plan_upload_model(lfm_plan *plan, const lfm_model *model);
+/* The same without waiting for the copies to finish: the arrays must stay untouched until the next
+ * call on this plan that synchronises (lfm_plan_epoch*, lfm_plan_download, lfm_plan_check_finite);
+ * the next lfm_plan_epoch packs its interaction tuples while the copies are still in flight. */
+int lfm_plan_upload_model_async(lfm_plan *plan, const lfm_model *model);
 /* Device address and element count of one resident state array (for the caller's own
  * collectives): which = 0..5 item {w,g,m,b,bg,bm}, 6..11 user {w,g,m,b,bg,bm}. */
 int lfm_plan_table(lfm_plan *plan, int32_t which, void **dev_ptr, int64_t *count);

@@ -113,6 +113,7 @@ LIB_ONLY = {
     "lfm_plan_delta_apply": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_double)]),
     "lfm_plan_download": (C.c_int, [C.c_void_p, ModelP]),
     "lfm_plan_upload_model": (C.c_int, [C.c_void_p, ModelP]),
+    "lfm_plan_upload_model_async": (C.c_int, [C.c_void_p, ModelP]),
     "lfm_evaluate_ranks": (C.c_int, [CsrP, CsrP, CsrP, CsrP, ModelP, C.c_int32, c_i32p, c_f32p, c_f32p,
                                      C.c_int32]),
     "lfm_recommend": (C.c_int, [CsrP, CsrP, CsrP, c_i32p, C.c_int64, C.c_int32, C.c_int32, ModelP,

@@ -339,10 +339,15 @@ class ResidentPlan(object):
     def download(self):
         _check(_lib.lfm_plan_download(self._handle, self._lightfm.ptr))
 
-    def upload_model(self, lightfm):
+    def upload_model(self, lightfm, wait=True):
         """Refresh the resident state from the arrays of `lightfm` (same shapes as the plan's);
-        later ``download()`` calls write into these arrays."""
-        _check(_lib.lfm_plan_upload_model(self._handle, lightfm.ptr))
+        later ``download()`` calls write into these arrays.  ``wait=False``: return while the copies
+        are in flight (the next ``epoch`` packs its tuples beside them); the arrays must not be
+        touched before that call returns."""
+        if wait:
+            _check(_lib.lfm_plan_upload_model(self._handle, lightfm.ptr))
+        else:
+            _check(_lib.lfm_plan_upload_model_async(self._handle, lightfm.ptr))
         self._lightfm = lightfm
 
     def all_finite(self):

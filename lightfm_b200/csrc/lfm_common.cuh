@@ -104,7 +104,9 @@ cudaError_t lfm_launch_replay(int loss, const FitArgs& a, cudaStream_t st);
 // Bytes of FitArgs::replay_scratch the dataflow replay path wants for (loss, a); 0: not applicable.
 size_t lfm_replay_dataflow_scratch_bytes(int loss, const FitArgs& a, int64_t bitmap_limit_bytes);
 cudaError_t lfm_launch_hogwild(int loss, const FitArgs& a, Tuple* tuples, cudaStream_t st,
-                               int* launches, cudaEvent_t ev_train_begin, cudaEvent_t ev_train_end);
+                               int* launches, cudaEvent_t ev_train_begin, cudaEvent_t ev_train_end,
+                               cudaStream_t pack_stream = nullptr, cudaEvent_t pack_after = nullptr,
+                               cudaEvent_t pack_done = nullptr);
 // tuples[i] = {user, item, weight, y}[order[i]]; order = a.shuffle when given, else a Feistel permutation keyed by perm_key
 cudaError_t lfm_launch_pack(const FitArgs& a, int loss, Tuple* tuples, uint32_t perm_key, cudaStream_t st);
 cudaError_t lfm_launch_regularize(const DevModel& m, DevScales* scales, cudaStream_t st);

@@ -1084,8 +1084,22 @@ cudaError_t lfm_launch_pack(const FitArgs& a, int loss, Tuple* tuples, uint32_t 
 // Runs one epoch in hogwild mode.  With L2 regularisation the epoch is cut into
 // segments so the host-visible rescale check (T:901-904) happens between launches.
 cudaError_t lfm_launch_hogwild(int loss, const FitArgs& a, Tuple* tuples, cudaStream_t st,
-                               int* launches, cudaEvent_t ev_train_begin, cudaEvent_t ev_train_end) {
-    cudaError_t e = lfm_launch_pack(a, loss, tuples, a.seed ^ 0x5bd1e995u, st);
+                               int* launches, cudaEvent_t ev_train_begin, cudaEvent_t ev_train_end,
+                               cudaStream_t pack_stream, cudaEvent_t pack_after, cudaEvent_t pack_done) {
+    cudaError_t e;
+    if (pack_stream) {
+        // pack_kernel only reads the interaction list: it runs on a side stream under whatever the main
+        // stream is still doing (the model state's H2D copies), after `pack_after`
+        e = cudaStreamWaitEvent(pack_stream, pack_after, 0);
+        if (e != cudaSuccess) return e;
+        e = lfm_launch_pack(a, loss, tuples, a.seed ^ 0x5bd1e995u, pack_stream);
+        if (e != cudaSuccess) return e;
+        e = cudaEventRecord(pack_done, pack_stream);
+        if (e != cudaSuccess) return e;
+        e = cudaStreamWaitEvent(st, pack_done, 0);
+    } else {
+        e = lfm_launch_pack(a, loss, tuples, a.seed ^ 0x5bd1e995u, st);
+    }
     if (e != cudaSuccess) return e;
     if (launches) (*launches)++;
     bool reg = (a.item_alpha != 0.0 || a.user_alpha != 0.0);

@@ -51,6 +51,8 @@ typedef std::unordered_map<std::string, Buf> Arena;
 Arena g_arena;
 Arena* g_cur = &g_arena;  // arena the staging helpers allocate from (global, or a plan's own)
 cudaStream_t g_stream = nullptr;
+cudaStream_t g_stream2 = nullptr;  // side stream: pack_kernel under the model state's upload (plans)
+cudaEvent_t g_ev_side[2] = {nullptr, nullptr};
 cudaEvent_t g_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 bool g_init = false;
 bool g_scoring_timed = false;  // g_ev[4..5] bracket the kernels of the last scoring call
@@ -66,6 +68,8 @@ int ensure_init() {
     }
     CU(cudaSetDevice(g_device));
     CU(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&g_stream2, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&g_ev_side[i], cudaEventDisableTiming));
     for (int i = 0; i < 6; i++) CU(cudaEventCreate(&g_ev[i]));
     g_init = true;
     return LFM_OK;
@@ -448,7 +452,7 @@ int stage_fit(int loss, const FitInputs& in, bool with_shuffle, Staged* out) {
 }
 
 // Launch one epoch on staged (device-resident) data.
-int run_fit(Staged& st, int mode, uint32_t seed, int* launches) {
+int run_fit(Staged& st, int mode, uint32_t seed, int* launches, bool pack_aside = false) {
     FitArgs& a = st.a;
     a.seed = seed;
     CU(cudaMemsetAsync(a.counters, 0, sizeof(DevCounters), g_stream));
@@ -486,7 +490,8 @@ int run_fit(Staged& st, int mode, uint32_t seed, int* launches) {
         void* p = nullptr;
         int rc = arena_get("fit.tuples", sizeof(Tuple) * (size_t)(a.n > 0 ? a.n : 1), &p);
         if (rc != LFM_OK) return rc;
-        CU(lfm_launch_hogwild(st.loss, a, (Tuple*)p, g_stream, launches, g_ev[4], g_ev[5]));
+        CU(lfm_launch_hogwild(st.loss, a, (Tuple*)p, g_stream, launches, g_ev[4], g_ev[5],
+                              pack_aside ? g_stream2 : nullptr, g_ev_side[0], g_ev_side[1]));
     }
     return LFM_OK;
 }
@@ -941,6 +946,7 @@ struct lfm_plan {
     int loss = 0;
     int nkos = 0;
     bool has_shuffle_buf = false;
+    bool upload_in_flight = false;  // lfm_plan_upload_model_async: g_ev_side[0] marks the stream position before it
     // delta exchange of a replicated table (lfm_plan_delta_*): per side (0 item, 1 user)
     DeltaSegs segs[2] = {};
     float* dS[2] = {nullptr, nullptr};
@@ -1074,7 +1080,10 @@ static int plan_epoch_impl(lfm_plan* p, const int32_t* shuffle_indices, uint32_t
     }
     CU(cudaEventRecord(g_ev[1], g_stream));
     int launches = 0;
-    int rc = run_fit(st, mode, seed, &launches);
+    // an asynchronous model upload is still on the stream: let pack_kernel run beside it
+    const bool aside = p->upload_in_flight && mode == LFM_MODE_HOGWILD && !shuffle_indices;
+    p->upload_in_flight = false;
+    int rc = run_fit(st, mode, seed, &launches, aside);
     if (rc != LFM_OK) return rc;
     CU(cudaEventRecord(g_ev[2], g_stream));
     DevCounters hc;
@@ -1177,7 +1186,7 @@ extern "C" int lfm_plan_delta_apply(lfm_plan* p, int32_t side, double* ms) {
 
 // Refresh the resident model state (and the scalar hyper-parameters) from the caller's arrays;
 // the interactions, feature matrices and positives lookup stay as uploaded.
-extern "C" int lfm_plan_upload_model(lfm_plan* p, const lfm_model* model) {
+static int plan_upload_model_impl(lfm_plan* p, const lfm_model* model, bool wait) {
     std::lock_guard<std::mutex> lock(g_mu);
     if (!p || !model) return fail(LFM_ERR_ARG, "null plan / model");
     const DevModel& dm = p->st.a.model;
@@ -1189,12 +1198,20 @@ extern "C" int lfm_plan_upload_model(lfm_plan* p, const lfm_model* model) {
     struct Restore { ~Restore() { g_cur = &g_arena; } } restore;
     Xfer x;
     DevModel fresh;
+    if (!wait) CU(cudaEventRecord(g_ev_side[0], g_stream));  // everything before the state copies
     int rc = upload_model(model, true, &fresh, x);
     if (rc != LFM_OK) return rc;
     p->st.a.model = fresh;
-    CU(cudaStreamSynchronize(g_stream));
+    if (wait) CU(cudaStreamSynchronize(g_stream));
+    p->upload_in_flight = !wait;
     return LFM_OK;
 }
+
+extern "C" int lfm_plan_upload_model(lfm_plan* p, const lfm_model* model) { return plan_upload_model_impl(p, model, true); }
+// The same without waiting for the copies: the arrays must stay untouched until the next call on
+// this plan that synchronises (lfm_plan_epoch*, lfm_plan_download, lfm_plan_check_finite).  The
+// next lfm_plan_epoch runs its pack_kernel beside the copies.
+extern "C" int lfm_plan_upload_model_async(lfm_plan* p, const lfm_model* model) { return plan_upload_model_impl(p, model, false); }
 
 // Page-lock / unlock caller-owned host memory (cudaHostRegister) so that the copies of a
 // long-lived buffer (the model's numpy arrays across fit_partial calls) run at PCIe speed.

@@ -413,7 +413,7 @@ class LightFM(object):
         if cache.plan is None:
             cache.plan = self._make_plan(item_features, user_features, interactions, sample_weight, state)
         else:
-            cache.plan.upload_model(state)
+            cache.plan.upload_model(state, wait=False)  # the first epoch's pack kernel runs beside the copies
         plan = cache.plan
         finite = True
         try:

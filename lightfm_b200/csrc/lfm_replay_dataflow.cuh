@@ -107,11 +107,15 @@ struct RdfPipe {
     volatile int32_t a_prod, a_cons, b_prod, b_cons;  // chunk counters of the two rings
 };
 
-__device__ __forceinline__ void rdf_wait_ge(volatile int32_t* flag, int v, long long& waited) {
+// `fence`: a block-scope fence after the flag has been seen.  Stage V passes false: a fence there would
+// wait for its outstanding (prefetching) global loads; it relies on the SM executing the shared-memory
+// accesses of its warps in issue order (volatile flags, __syncwarp between data and flag), as the
+// other side of each hand-off still fences.
+__device__ __forceinline__ void rdf_wait_ge(volatile int32_t* flag, int v, long long& waited, bool fence = true) {
     const long long t0 = clock64();
     if (threadIdx.x % 32 == 0)
         while (*flag < v) __nanosleep(64);
-    __threadfence_block();  // what the other stage wrote before the flag is read after it
+    if (fence) __threadfence_block();  // what the other stage wrote before the flag is read after it
     __syncwarp();
     waited += clock64() - t0;
 }
@@ -328,22 +332,34 @@ __device__ __forceinline__ void rdf_stage_version(const FitArgs& a, const RdfScr
         }
         __syncwarp();
     }
-    for (int chunk = 0; chunk < nchunks; chunk++) {
-        rdf_wait_ge(&pp->a_prod, chunk + 1, waited);
+    // A chunk's touch counters are requested right after the previous chunk has stored its own
+    // (same SM: the loads see those stores), so their latency runs under the hand-off to stage E
+    // instead of at the head of the next iteration.
+    int user = -1, item = 0, neg = -1, eu = 0, ei = 0, en = 0;
+    float w = 0.f, y = 0.f;
+    auto take = [&](int chunk) {  // read chunk `chunk` from ring A (it must be there), free its slot, request its counters
         const RdfChunkA& in = pp->a[chunk % RDF_PIPE];
-        const int user = in.user[lane], item = in.item[lane], neg = in.neg[lane];
-        const float w = in.w[lane], y = in.y[lane];
+        user = in.user[lane]; item = in.item[lane]; neg = in.neg[lane];
+        w = in.w[lane]; y = in.y[lane];
         __syncwarp();
         if (lane == 0) pp->a_cons = chunk + 1;
-        const bool valid = user >= 0;
-        const unsigned V = __ballot_sync(LFM_FULL, valid);
-        // touch counters of my rows as the earlier chunks left them
-        int eu = 0, ei = 0, en = 0;
-        if (valid) {
+        eu = ei = en = 0;
+        if (user >= 0) {
             eu = cnt_user[user];
             ei = cnt_item[item];
             if (LOSS == LOSS_BPR && neg >= 0) en = cnt_item[neg];
         }
+    };
+    bool have = false;  // chunk `chunk` was already taken at the end of the previous iteration
+    for (int chunk = 0; chunk < nchunks; chunk++) {
+        if (!have) {
+            rdf_wait_ge(&pp->a_prod, chunk + 1, waited, false);
+            take(chunk);
+        }
+        const int cur_user = user, cur_item = item, cur_neg = neg;
+        const float cur_w = w, cur_y = y;
+        const bool valid = user >= 0;
+        const unsigned V = __ballot_sync(LFM_FULL, valid);
         // versions: + touches by the lanes below me; and am I the last lane of the chunk on each row
         bool lu = true, li = true, ln = true;
         {
@@ -398,13 +414,25 @@ __device__ __forceinline__ void rdf_stage_version(const FitArgs& a, const RdfScr
             if (li) cnt_item[item] = ei + 1;
             if (LOSS == LOSS_BPR && neg >= 0 && ln) cnt_item[neg] = en + 1;
         }
+        const int out_eu = eu, out_ei = ei, out_en = en;
+        __syncwarp();  // the stores above are ordered before the next chunk's counter loads
+        // the next chunk, if stage S has it ready: take it now
+        have = false;
+        if (LOSS == LOSS_BPR && chunk + 1 < nchunks) {  // (logistic: measured slower, its version step is two match.any)
+            int ready = 0;
+            if (lane == 0) ready = pp->a_prod >= chunk + 2;
+            ready = __shfl_sync(LFM_FULL, ready, 0);
+            if (ready) {
+                take(chunk + 1);
+                have = true;
+            }
+        }
         // hand the chunk to stage E
-        rdf_wait_ge(&pp->b_cons, chunk - (RDF_PIPE - 1), waited);
+        rdf_wait_ge(&pp->b_cons, chunk - (RDF_PIPE - 1), waited, false);
         RdfChunkB& o = pp->b[chunk % RDF_PIPE];
-        o.user[lane] = user; o.item[lane] = item; o.neg[lane] = neg;
-        o.eu[lane] = eu; o.ei[lane] = ei; o.en[lane] = en;
-        o.w[lane] = w; o.y[lane] = y;
-        __threadfence_block();
+        o.user[lane] = cur_user; o.item[lane] = cur_item; o.neg[lane] = cur_neg;
+        o.eu[lane] = out_eu; o.ei[lane] = out_ei; o.en[lane] = out_en;
+        o.w[lane] = cur_w; o.y[lane] = cur_y;
         __syncwarp();  // also: counters (same SM: shared memory / L1) written before the next chunk reads them
         if (lane == 0) pp->b_prod = chunk + 1;
     }

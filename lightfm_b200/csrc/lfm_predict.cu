@@ -524,6 +524,88 @@ __global__ void __launch_bounds__(256) topk_select_kernel(const float* __restric
     }
 }
 
+// Small k (<= TOPK_SMALL): ONE pass over the row.  Every thread keeps the TOPK_SMALL best
+// (key, item) pairs of its strided share in registers (an insertion happens only when an element
+// beats the thread's current worst: ~k ln(n / 256 k) times per thread), then the CTA extracts the
+// k global winners one by one: block-wide arg-max over the threads' current best, the winner pops
+// it.  Order and ties as in the radix path: key descending, item id ascending.
+#define TOPK_SMALL 16
+__global__ void __launch_bounds__(256) topk_small_kernel(const float* __restrict__ scores, int ld, int n_items,
+                                                         int n_users, int k, int32_t* out_items, float* out_scores) {
+    __shared__ unsigned long long warp_best[8];
+    __shared__ unsigned long long s_best;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int row = blockIdx.x; row < n_users; row += gridDim.x) {
+        const float* sc = scores + (size_t)row * ld;
+        uint32_t key[TOPK_SMALL];
+        int32_t idx[TOPK_SMALL];
+#pragma unroll
+        for (int j = 0; j < TOPK_SMALL; j++) { key[j] = 0u; idx[j] = 0x7fffffff; }
+        auto offer = [&](uint32_t kx, int32_t i) {
+            if (kx > key[TOPK_SMALL - 1]) {  // ids arrive in ascending order: an equal key never displaces
+                uint32_t ck = kx;
+                int32_t ci = i;
+#pragma unroll
+                for (int j = 0; j < TOPK_SMALL; j++) {  // insert, keeping (key desc, id asc)
+                    if (ck > key[j]) {
+                        const uint32_t tk = key[j]; const int32_t ti = idx[j];
+                        key[j] = ck; idx[j] = ci;
+                        ck = tk; ci = ti;
+                    }
+                }
+            }
+        };
+        // four consecutive items per thread per step (rows are padded to a multiple of 4 and 16 B-aligned),
+        // two steps in flight
+        const float4* sc4 = (const float4*)sc;
+        const int n4 = ld >> 2;
+        for (int q0 = threadIdx.x; q0 < n4; q0 += 2 * blockDim.x) {
+            const int q1 = q0 + blockDim.x;
+            const float4 a4 = __ldcs(sc4 + q0);
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (q1 < n4) b4 = __ldcs(sc4 + q1);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int e = 0; e < 4; e++)
+                if (4 * q0 + e < n_items) offer(score_key(av[e]), 4 * q0 + e);
+            if (q1 < n4) {
+#pragma unroll
+                for (int e = 0; e < 4; e++)
+                    if (4 * q1 + e < n_items) offer(score_key(bv[e]), 4 * q1 + e);
+            }
+        }
+        for (int r = 0; r < k; r++) {
+            // (key, smaller id first) as one 64-bit value; 0 = nothing left / not scorable
+            unsigned long long v = key[0] ? (((unsigned long long)key[0] << 32) | (uint32_t)(0x7fffffff - idx[0])) : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long ov = __shfl_xor_sync(LFM_FULL, v, o);
+                v = ov > v ? ov : v;
+            }
+            if (lane == 0) warp_best[w] = v;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned long long b = warp_best[0];
+                for (int ww = 1; ww < 8; ww++) b = warp_best[ww] > b ? warp_best[ww] : b;
+                s_best = b;
+            }
+            __syncthreads();
+            const unsigned long long best = s_best;
+            const int32_t bi = best ? (int32_t)(0x7fffffff - (uint32_t)(best & 0xffffffffull)) : -1;
+            if (best && key[0] == (uint32_t)(best >> 32) && idx[0] == bi) {  // mine: pop it
+#pragma unroll
+                for (int j = 0; j + 1 < TOPK_SMALL; j++) { key[j] = key[j + 1]; idx[j] = idx[j + 1]; }
+                key[TOPK_SMALL - 1] = 0u; idx[TOPK_SMALL - 1] = 0x7fffffff;
+            }
+            if (threadIdx.x == 0) {  // fewer than k scorable items: pad with -1 / NaN
+                out_items[(size_t)row * k + r] = bi;
+                out_scores[(size_t)row * k + r] = bi >= 0 ? sc[bi] : __int_as_float(0x7fc00000);
+            }
+            __syncthreads();  // s_best / warp_best are rewritten in the next round
+        }
+    }
+}
+
 __global__ void in_positives_kernel(DevCsr mat, int row, int col, int32_t* out) {
     int lane = threadIdx.x;
     bool a = lfm_warp_member(mat.indices, mat.indptr[row], mat.indptr[row + 1], col, lane);
@@ -656,7 +738,8 @@ cudaError_t lfm_launch_recommend(const DevCsr& itf, const DevCsr& usf, const Dev
     if (exclude && exclude->nnz > 0)
         exclude_kernel<<<(int)(((int64_t)n_users * 32 + 255) / 256), 256, 0, st>>>(*exclude, user_ids, n_users, n_items, ld, scores);
     int g2 = n_users < 148 * 8 ? n_users : 148 * 8;
-    topk_select_kernel<<<g2, 256, 0, st>>>(scores, ld, n_items, n_users, k, out_items, out_scores);
+    if (k <= TOPK_SMALL) topk_small_kernel<<<g2, 256, 0, st>>>(scores, ld, n_items, n_users, k, out_items, out_scores);
+    else topk_select_kernel<<<g2, 256, 0, st>>>(scores, ld, n_items, n_users, k, out_items, out_scores);
     if (launches) *launches += 4;
     return cudaGetLastError();
 }

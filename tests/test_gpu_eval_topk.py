@@ -104,7 +104,8 @@ def test_row_sort_and_auc_match_oracle_for_all_row_lengths():
     assert np.array_equal(outs[0][1], outs[1][1])
 
 
-@pytest.mark.parametrize("n_items,d,k", [(1003, 10, 10), (5000, 64, 100), (37, 16, 64)])
+@pytest.mark.parametrize("n_items,d,k", [(1003, 10, 10), (5000, 64, 100), (37, 16, 64), (5000, 32, 16), (1003, 10, 1),
+                                          (9, 8, 16), (20011, 16, 7)])
 def test_recommend_equals_argsort_of_predict(n_items, d, k):
     n_users = 120
     model = _model(n_users, n_items, d, 4)

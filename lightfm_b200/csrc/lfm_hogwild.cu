@@ -792,11 +792,17 @@ __global__ void __launch_bounds__(HOT ? 512 : 256) hogwild_kernel(FitArgs a, con
                 while (sampled < m.max_sampled) {
                     sampled++;
                     int cand = lfm_bounded(next_u32(), (uint32_t)n_items);
+                    // with a resident plan's positives bitmap the candidate's membership word leaves
+                    // before its gather: a violating candidate then needs no search afterwards
+                    uint32_t wm = 0u;
+                    if (a.pos_bitmap) wm = __ldg(a.pos_bitmap + (size_t)user * a.bitmap_words + (cand >> 5));
                     GATHER(a.itf, m.item, a.hot_slot_item, cand, item_scale, q, fr_q);
                     float np = dot<KPL>(u, q);
                     c_neg++;
                     if (np > pp - 1.0f) {
-                        if (lfm_warp_member(a.pos.indices, ps, pe, cand, lane)) { c_rej++; continue; }
+                        const bool member = a.pos_bitmap ? ((wm >> (cand & 31)) & 1u) != 0u
+                                                         : lfm_warp_member(a.pos.indices, ps, pe, cand, lane);
+                        if (member) { c_rej++; continue; }
                         float l = __ldg(a.loss_table_f + sampled);
                         loss = (LOSS == LOSS_KOS) ? l : tp.weight * l;
                         if (loss > (float)LFM_MAX_LOSS) loss = (float)LFM_MAX_LOSS;

@@ -96,6 +96,7 @@ __device__ __forceinline__ float rank_score(const float* __restrict__ ut, int sl
 // table.  Per component: one float4 of item values (coalesced), two broadcast float4 loads of the
 // eight users' values, 32 multiplies + 32 adds: the FP32 pipe is the limiter, not the LSU (the first
 // version read the eight user values with eight scalar shared loads per 16 flops).
+template <int UNR = 4>
 __device__ __forceinline__ void tile_scores(const float* __restrict__ ut, const float* __restrict__ irt,
                                             int ld, int d, int i, float (&acc)[RANK_IT][RANK_UT]) {
     const float4 vb = *(const float4*)(irt + (size_t)d * ld + i);
@@ -106,7 +107,7 @@ __device__ __forceinline__ void tile_scores(const float* __restrict__ ut, const 
     for (int k = 0; k < RANK_IT; k++)
 #pragma unroll
         for (int u = 0; u < RANK_UT; u++) acc[k][u] = ub[u] + vbb[k];
-#pragma unroll 4
+#pragma unroll UNR
     for (int j = 0; j < d; j++) {
         const float4 v4 = *(const float4*)(irt + (size_t)j * ld + i);
         const float4 u0 = *(const float4*)(ut + j * RANK_UT), u1 = *(const float4*)(ut + j * RANK_UT + 4);
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(RANK_G * RANK_GT, 1) predict_ranks_tiled_kerne
             for (int i0 = 0; i0 < n_items; i0 += RANK_GT * RANK_IT) {
                 const int i = i0 + tl * RANK_IT;
                 float acc[RANK_IT][RANK_UT];
-                if (i < ld) tile_scores(ut, irt, ld, d, i, acc);
+                if (i < ld) tile_scores<(RANK_G == 2 ? 8 : 4)>(ut, irt, ld, d, i, acc);
                 const float ninf = __int_as_float(0xff800000);
 #pragma unroll
                 for (int k = 0; k < RANK_IT; k++)
@@ -643,7 +644,7 @@ cudaError_t lfm_launch_predict(const DevCsr& itf, const DevCsr& usf, const DevMo
 static std::atomic<int> g_rank_groups{1};
 extern "C" int lfm_set_rank_groups(int groups) {
     int old = g_rank_groups.load();
-    if (groups == 1 || groups == 3) g_rank_groups.store(groups);
+    if (groups >= 1 && groups <= 3) g_rank_groups.store(groups);
     return old;
 }
 
@@ -665,7 +666,14 @@ cudaError_t lfm_launch_predict_ranks(const DevCsr& itf, const DevCsr& usf, const
     compact_users_kernel<<<(test.rows + 255) / 256, 256, 0, st>>>(test, active, count);
     const size_t per_group = (size_t)RANK_UT * (m.d + 1) + RANK_UT * RANK_TCH * 3 + RANK_UT * RANK_UT * RANK_TCH;
     const size_t group_bytes = sizeof(float) * ((per_group + 3) & ~(size_t)3);
-    if (g_rank_groups.load() == 3) {
+    if (g_rank_groups.load() == 2) {
+        const size_t smem = 2 * group_bytes;
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(predict_ranks_tiled_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int grid = (test.rows + RANK_UT * 2 - 1) / (RANK_UT * 2);
+        if (grid > 148) grid = 148;  // one persistent CTA (two user tiles, 128 registers per thread) per SM
+        predict_ranks_tiled_kernel<2><<<grid, 2 * RANK_GT, smem, st>>>(usf, test, train, m, repr_t, ld, active, count, ranks);
+    } else if (g_rank_groups.load() == 3) {
         const size_t smem = 3 * group_bytes;
         if (smem > 48 * 1024)
             cudaFuncSetAttribute(predict_ranks_tiled_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -159,7 +159,7 @@ def test_predict_ranks_register_tiled_kernel_odd_shapes():
     assert np.array_equal(outs[0], outs[1])
 
 
-@pytest.mark.parametrize("groups", (1, 3))
+@pytest.mark.parametrize("groups", (1, 2, 3))
 def test_predict_ranks_dense_test_rows_both_tilings(groups):
     """The reference's tests/test_api.py::test_predict_ranks scenario (every item of every user is a
     test interaction: 100 > 64 test entries per user, i.e. two chunks per tile), repeated over seeds

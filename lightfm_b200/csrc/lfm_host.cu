@@ -490,6 +490,25 @@ int run_fit(Staged& st, int mode, uint32_t seed, int* launches, bool pack_aside 
         void* p = nullptr;
         int rc = arena_get("fit.tuples", sizeof(Tuple) * (size_t)(a.n > 0 ? a.n : 1), &p);
         if (rc != LFM_OK) return rc;
+        // The boundary call (no resident plan): build the exact membership bitmap of the positives for
+        // this epoch when it fits -- one sweep over the CSR just uploaded (~0.5 ms at C2) buys the
+        // slot kernels a one-load membership test instead of a search per violating negative.
+        if (!a.pos_bitmap && a.pos.indptr && st.loss != LOSS_LOGISTIC && g_bitmap_limit_bytes > 0 && a.n >= (1 << 20) &&
+            lfm_fast_path_eligible(st.loss, a, a.n)) {
+            const int64_t n_cols = a.pos.cols > a.itf.rows ? a.pos.cols : a.itf.rows;
+            const int64_t words = (n_cols + 31) / 32;
+            const int64_t bytes = words * 4 * (int64_t)a.pos.rows;
+            // worth it only when the sweep over the bitmap is small next to the epoch itself
+            if (a.pos.rows > 0 && words > 0 && bytes <= g_bitmap_limit_bytes && bytes <= 64 * a.n) {
+                void* bm = nullptr;
+                rc = arena_get("fit.bitmap", (size_t)bytes, &bm);
+                if (rc != LFM_OK) return rc;
+                CU(lfm_launch_build_bitmap(a.pos, (uint32_t*)bm, (int32_t)words, g_stream));
+                a.pos_bitmap = (const uint32_t*)bm;
+                a.bitmap_words = (int32_t)words;
+                (*launches)++;
+            }
+        }
         CU(lfm_launch_hogwild(st.loss, a, (Tuple*)p, g_stream, launches, g_ev[4], g_ev[5],
                               pack_aside ? g_stream2 : nullptr, g_ev_side[0], g_ev_side[1]));
     }

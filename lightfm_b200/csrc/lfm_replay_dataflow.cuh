@@ -661,8 +661,8 @@ __device__ __forceinline__ void rdf_execute(const FitArgs& a, const RdfScratch& 
     }
 }
 
-// CTA 0: its first warp is the scheduler (the rest of that SM stays idle so that the one
-// sequential warp of the epoch owns the SM's issue slots); every other CTA: RDF_WARPS executors.
+// CTA 0: its first three warps are the scheduler's stages (the rest of that SM stays idle so that
+// the epoch's sequential part owns the SM's issue slots); every other CTA: RDF_WARPS executors.
 template <int LOSS, int K, int AD>
 __global__ void __launch_bounds__(RDF_WARPS * 32) rdf_kernel(FitArgs a, RdfScratch s) {
     extern __shared__ __align__(16) float rdf_smem[];
@@ -708,7 +708,7 @@ static size_t rdf_scratch_bytes(int loss, const FitArgs& a, int64_t bitmap_limit
 }
 
 static cudaEvent_t g_rdf_ev[2] = {nullptr, nullptr};
-static double g_rdf_ms[2] = {0.0, 0.0};  // scheduler warp, whole kernel of the last dataflow epoch
+static double g_rdf_ms[2] = {0.0, 0.0};  // scheduler (its emit stage's lifetime), whole kernel of the last dataflow epoch
 static int g_rdf_tasks = -1;
 
 // Returns cudaErrorNotSupported when the epoch has to run in replay_kernel instead (out of scope);

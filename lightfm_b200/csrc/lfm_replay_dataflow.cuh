@@ -249,20 +249,30 @@ __device__ __forceinline__ void rdf_stage_sample(const FitArgs& a, const RdfScra
                 const int lim = lim64 > 64 ? 64 : (lim64 < 0 ? 0 : (int)lim64);
                 // resolve the lanes in order: incoming shift -> my rejections -> outgoing shift
                 const unsigned packed = M | ((unsigned)lim << 8);
-                const unsigned A = __ballot_sync(LFM_FULL, active);
-                int sft = 0, my_in = 0, over_lane = -1, over_s = 0;
-#pragma unroll 8
-                for (int j = 0; j < 32; j++) {
-                    const unsigned pj = __shfl_sync(LFM_FULL, packed, j);
-                    if (((A >> j) & 1u) && over_lane < 0) {
-                        if (j == lane) my_in = sft;
-                        const int run = __ffs(~((pj & 0xffu) >> sft)) - 1;  // consecutive member draws from draw k0 + sft
-                        const int lj = (int)(pj >> 8);
-                        const int v = sft + (run < lj ? run : lj);
-                        if (v > wuse - 1) { over_lane = j; over_s = sft; }
-                        else sft = v;
-                    }
+                // Only a lane whose draw at the current shift is a positive changes the shift, so the
+                // walk jumps from one such lane to the next: lane s keeps B_s = the lanes whose draw
+                // k0 + s is a member, and the next event is the lowest bit of B_shift at or above `cur`.
+                unsigned myB = 0u;
+#pragma unroll
+                for (int sb = 0; sb < RDF_W; sb++) {
+                    const unsigned b = __ballot_sync(LFM_FULL, active && ((M >> sb) & 1u));
+                    if (lane == sb) myB = b;
                 }
+                int sft = 0, my_in = 0, over_lane = -1, over_s = 0, cur = 0;
+                while (cur < 32) {
+                    const unsigned Bs = __shfl_sync(LFM_FULL, myB, sft) & ~((1u << cur) - 1u);
+                    if (Bs == 0u) break;
+                    const int j = __ffs(Bs) - 1;  // the next lane that rejects its first draw
+                    if (lane >= cur && lane <= j) my_in = sft;
+                    const unsigned pj = __shfl_sync(LFM_FULL, packed, j);
+                    const int run = __ffs(~((pj & 0xffu) >> sft)) - 1;  // consecutive member draws from draw k0 + sft
+                    const int lj = (int)(pj >> 8);
+                    const int v = sft + (run < lj ? run : lj);
+                    if (v > wuse - 1) { over_lane = j; over_s = sft; break; }
+                    sft = v;
+                    cur = j + 1;
+                }
+                if (over_lane < 0 && lane >= cur) my_in = sft;
                 const bool kept = active && (over_lane < 0 || lane < over_lane);
                 bool kept_mem = false;
                 if (kept) {

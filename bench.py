@@ -423,12 +423,15 @@ def run_ours(args):
     # -- value: resident plan, kernels only --------------------------------------------------
     plan = fast.ResidentPlan("warp", itf, usf, pos, prob.row, prob.col, prob.data, prob.data,
                              holder, 0.0, 0.0)
+    # consecutive epochs of one fit: each epoch tells the library the next one's seed, whose pack kernel
+    # then runs beside this epoch's SGD kernel (lfm_plan_epoch_next)
     for w in range(args.warmup):
-        plan.epoch(seed=1000 + w, num_threads=threads)
+        plan.epoch(seed=1000 + w, num_threads=threads, next_seed=1000 + w + 1 if w + 1 < args.warmup else 2000)
     torch.cuda.synchronize()
     clocks.mark(True)
     t0 = time.perf_counter()
-    counters = [plan.epoch(seed=2000 + s, num_threads=threads) for s in range(args.steps)]
+    counters = [plan.epoch(seed=2000 + s, num_threads=threads, next_seed=2000 + s + 1 if s + 1 < args.steps else None)
+                for s in range(args.steps)]
     torch.cuda.synchronize()
     wall_resident = time.perf_counter() - t0
     clocks.mark(False)

@@ -263,6 +263,11 @@ int lfm_plan_create(lfm_plan **out, int32_t loss, const lfm_csr *item_features,
  * permutation keyed by `seed` replaces the host shuffle of lightfm.py:689-690. */
 int lfm_plan_epoch(lfm_plan *plan, const int32_t *shuffle_indices, uint32_t seed,
                    int32_t num_threads, lfm_counters *counters);
+/* lfm_plan_epoch (device-generated order) that is also told the seed of the epoch to follow: the
+ * following epoch's interaction tuples are packed on a side stream while this epoch trains, and the
+ * next lfm_plan_epoch* call with seed == next_seed starts its SGD kernel at once. */
+int lfm_plan_epoch_next(lfm_plan *plan, uint32_t seed, uint32_t next_seed, int32_t num_threads,
+                        lfm_counters *counters);
 /* One pass over interactions [begin, begin + count) of the uploaded list (count < 0: to the end) in
  * a device-generated random order; hogwild mode only.  Lets a caller cut an epoch into phases. */
 int lfm_plan_epoch_range(lfm_plan *plan, uint32_t seed, int32_t num_threads, int64_t begin,

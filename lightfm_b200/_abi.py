@@ -106,6 +106,7 @@ LIB_ONLY = {
                                   c_f32p, c_f32p, C.c_int64, ModelP, C.c_double, C.c_double,
                                   C.c_int32, C.c_int32]),
     "lfm_plan_epoch": (C.c_int, [C.c_void_p, c_i32p, C.c_uint32, C.c_int32, CountersP]),
+    "lfm_plan_epoch_next": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int32, CountersP]),
     "lfm_plan_epoch_range": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int32, C.c_int64, C.c_int64, CountersP]),
     "lfm_plan_delta_begin": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.POINTER(C.c_double)]),
     "lfm_plan_delta_make": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64),

@@ -299,7 +299,14 @@ class ResidentPlan(object):
             _abi.f32p(sample_weight) if sample_weight is not None else null_f,
             n_ex, lightfm.ptr, float(item_alpha), float(user_alpha), int(k), int(n)))
 
-    def epoch(self, seed, num_threads=2, shuffle_indices=None):
+    def epoch(self, seed, num_threads=2, shuffle_indices=None, next_seed=None):
+        """One epoch.  ``next_seed``: the seed the following ``epoch`` call will use (device-generated
+        order only) -- its tuples are packed beside this epoch's SGD kernel."""
+        if next_seed is not None and shuffle_indices is None:
+            cnt = _abi.LfmCounters()
+            _check(_lib.lfm_plan_epoch_next(self._handle, int(seed) & 0xFFFFFFFF, int(next_seed) & 0xFFFFFFFF,
+                                            int(num_threads), ctypes.byref(cnt)))
+            return cnt.as_dict()
         if shuffle_indices is not None:
             _abi._require(shuffle_indices, np.int32, 1, "shuffle_indices")
             if len(shuffle_indices) != len(self._args[4]):

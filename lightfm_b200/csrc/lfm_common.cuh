@@ -106,7 +106,7 @@ size_t lfm_replay_dataflow_scratch_bytes(int loss, const FitArgs& a, int64_t bit
 cudaError_t lfm_launch_hogwild(int loss, const FitArgs& a, Tuple* tuples, cudaStream_t st,
                                int* launches, cudaEvent_t ev_train_begin, cudaEvent_t ev_train_end,
                                cudaStream_t pack_stream = nullptr, cudaEvent_t pack_after = nullptr,
-                               cudaEvent_t pack_done = nullptr);
+                               cudaEvent_t pack_done = nullptr, bool prepacked = false);
 // tuples[i] = {user, item, weight, y}[order[i]]; order = a.shuffle when given, else a Feistel permutation keyed by perm_key
 cudaError_t lfm_launch_pack(const FitArgs& a, int loss, Tuple* tuples, uint32_t perm_key, cudaStream_t st);
 cudaError_t lfm_launch_regularize(const DevModel& m, DevScales* scales, cudaStream_t st);

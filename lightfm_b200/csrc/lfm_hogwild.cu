@@ -1091,9 +1091,15 @@ cudaError_t lfm_launch_pack(const FitArgs& a, int loss, Tuple* tuples, uint32_t 
 // segments so the host-visible rescale check (T:901-904) happens between launches.
 cudaError_t lfm_launch_hogwild(int loss, const FitArgs& a, Tuple* tuples, cudaStream_t st,
                                int* launches, cudaEvent_t ev_train_begin, cudaEvent_t ev_train_end,
-                               cudaStream_t pack_stream, cudaEvent_t pack_after, cudaEvent_t pack_done) {
+                               cudaStream_t pack_stream, cudaEvent_t pack_after, cudaEvent_t pack_done,
+                               bool prepacked) {
     cudaError_t e;
-    if (pack_stream) {
+    if (prepacked) {
+        // `tuples` was packed for this epoch's seed on the side stream while the previous epoch trained
+        // (lfm_plan_epoch_next): wait for that kernel, launch nothing
+        e = cudaStreamWaitEvent(st, pack_done, 0);
+        if (launches) (*launches)--;  // (counted by the epoch that launched it)
+    } else if (pack_stream) {
         // pack_kernel only reads the interaction list: it runs on a side stream under whatever the main
         // stream is still doing (the model state's H2D copies), after `pack_after`
         e = cudaStreamWaitEvent(pack_stream, pack_after, 0);

@@ -53,6 +53,7 @@ Arena* g_cur = &g_arena;  // arena the staging helpers allocate from (global, or
 cudaStream_t g_stream = nullptr;
 cudaStream_t g_stream2 = nullptr;  // side stream: pack_kernel under the model state's upload (plans)
 cudaEvent_t g_ev_side[2] = {nullptr, nullptr};
+cudaEvent_t g_ev_prepack = nullptr;  // end of the pack kernel launched ahead for the next epoch (lfm_plan_epoch_next)
 cudaEvent_t g_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 bool g_init = false;
 bool g_scoring_timed = false;  // g_ev[4..5] bracket the kernels of the last scoring call
@@ -70,6 +71,7 @@ int ensure_init() {
     CU(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&g_stream2, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&g_ev_side[i], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&g_ev_prepack, cudaEventDisableTiming));
     for (int i = 0; i < 6; i++) CU(cudaEventCreate(&g_ev[i]));
     g_init = true;
     return LFM_OK;
@@ -452,7 +454,7 @@ int stage_fit(int loss, const FitInputs& in, bool with_shuffle, Staged* out) {
 }
 
 // Launch one epoch on staged (device-resident) data.
-int run_fit(Staged& st, int mode, uint32_t seed, int* launches, bool pack_aside = false) {
+int run_fit(Staged& st, int mode, uint32_t seed, int* launches, bool pack_aside = false, Tuple* prepacked = nullptr) {
     FitArgs& a = st.a;
     a.seed = seed;
     CU(cudaMemsetAsync(a.counters, 0, sizeof(DevCounters), g_stream));
@@ -509,8 +511,12 @@ int run_fit(Staged& st, int mode, uint32_t seed, int* launches, bool pack_aside 
                 (*launches)++;
             }
         }
-        CU(lfm_launch_hogwild(st.loss, a, (Tuple*)p, g_stream, launches, g_ev[4], g_ev[5],
-                              pack_aside ? g_stream2 : nullptr, g_ev_side[0], g_ev_side[1]));
+        if (prepacked)
+            CU(lfm_launch_hogwild(st.loss, a, prepacked, g_stream, launches, g_ev[4], g_ev[5], nullptr, nullptr,
+                                  g_ev_prepack, true));
+        else
+            CU(lfm_launch_hogwild(st.loss, a, (Tuple*)p, g_stream, launches, g_ev[4], g_ev[5],
+                                  pack_aside ? g_stream2 : nullptr, g_ev_side[0], g_ev_side[1]));
     }
     return LFM_OK;
 }
@@ -966,6 +972,11 @@ struct lfm_plan {
     int nkos = 0;
     bool has_shuffle_buf = false;
     bool upload_in_flight = false;  // lfm_plan_upload_model_async: g_ev_side[0] marks the stream position before it
+    // lfm_plan_epoch_next: the next epoch's tuples, packed on the side stream while this epoch trains
+    bool prepacked = false;
+    uint32_t prepacked_seed = 0;
+    int64_t prepacked_n = 0;
+    Tuple* prepacked_buf = nullptr;
     // delta exchange of a replicated table (lfm_plan_delta_*): per side (0 item, 1 user)
     DeltaSegs segs[2] = {};
     float* dS[2] = {nullptr, nullptr};
@@ -1061,6 +1072,7 @@ extern "C" int lfm_plan_create(lfm_plan** out, int32_t loss, const lfm_csr* item
 // One epoch on resident data.  shuffle_indices == NULL: the visiting order is a fresh
 // pseudo-random permutation generated on the device from `seed` (hogwild mode only).
 static int plan_epoch_impl(lfm_plan* p, const int32_t* shuffle_indices, uint32_t seed, int32_t num_threads,
+                           const uint32_t* next_seed,
                            int64_t begin, int64_t count, lfm_counters* counters) {
     std::lock_guard<std::mutex> lock(g_mu);
     if (!p) return fail(LFM_ERR_ARG, "null plan");
@@ -1102,8 +1114,35 @@ static int plan_epoch_impl(lfm_plan* p, const int32_t* shuffle_indices, uint32_t
     // an asynchronous model upload is still on the stream: let pack_kernel run beside it
     const bool aside = p->upload_in_flight && mode == LFM_MODE_HOGWILD && !shuffle_indices;
     p->upload_in_flight = false;
-    int rc = run_fit(st, mode, seed, &launches, aside);
+    const bool whole = begin == 0 && count == n_total;
+    // tuples packed ahead for exactly this epoch?  (anything else packed ahead is waited for and dropped)
+    Tuple* pre = nullptr;
+    if (p->prepacked) {
+        if (mode == LFM_MODE_HOGWILD && !shuffle_indices && whole && p->prepacked_seed == seed && p->prepacked_n == st.a.n)
+            pre = p->prepacked_buf;
+        else
+            CU(cudaStreamWaitEvent(g_stream, g_ev_prepack, 0));
+        p->prepacked = false;
+    }
+    int rc = run_fit(st, mode, seed, &launches, aside && !pre, pre);
     if (rc != LFM_OK) return rc;
+    if (next_seed && mode == LFM_MODE_HOGWILD && !shuffle_indices && whole && st.a.n > 0) {
+        // the next epoch's visiting order only depends on its seed: pack it now, beside this epoch's
+        // SGD kernel, into the tuple buffer this epoch is not reading
+        void *b0 = nullptr, *b1 = nullptr;
+        rc = arena_get("fit.tuples", sizeof(Tuple) * (size_t)st.a.n, &b0);
+        if (rc != LFM_OK) return rc;
+        rc = arena_get("fit.tuples2", sizeof(Tuple) * (size_t)st.a.n, &b1);
+        if (rc != LFM_OK) return rc;
+        Tuple* target = (pre == (Tuple*)b1) ? (Tuple*)b0 : (Tuple*)b1;  // this epoch reads `pre`, or b0 when it packed itself
+        CU(lfm_launch_pack(st.a, p->loss, target, *next_seed ^ 0x5bd1e995u, g_stream2));
+        CU(cudaEventRecord(g_ev_prepack, g_stream2));
+        launches++;
+        p->prepacked = true;
+        p->prepacked_seed = *next_seed;
+        p->prepacked_n = st.a.n;
+        p->prepacked_buf = target;
+    }
     CU(cudaEventRecord(g_ev[2], g_stream));
     DevCounters hc;
     CU(cudaMemcpyAsync(&hc, st.a.counters, sizeof(hc), cudaMemcpyDeviceToHost, g_stream));
@@ -1119,7 +1158,15 @@ static int plan_epoch_impl(lfm_plan* p, const int32_t* shuffle_indices, uint32_t
 
 extern "C" int lfm_plan_epoch(lfm_plan* p, const int32_t* shuffle_indices, uint32_t seed,
                               int32_t num_threads, lfm_counters* counters) {
-    return plan_epoch_impl(p, shuffle_indices, seed, num_threads, 0, -1, counters);
+    return plan_epoch_impl(p, shuffle_indices, seed, num_threads, nullptr, 0, -1, counters);
+}
+
+// lfm_plan_epoch in the device-generated order, told the seed of the epoch that will follow: that
+// epoch's pack kernel runs on a side stream beside this epoch's SGD kernel (into a second tuple
+// buffer), and the following lfm_plan_epoch* call with that seed finds its tuples ready.
+extern "C" int lfm_plan_epoch_next(lfm_plan* p, uint32_t seed, uint32_t next_seed, int32_t num_threads,
+                                   lfm_counters* counters) {
+    return plan_epoch_impl(p, nullptr, seed, num_threads, &next_seed, 0, -1, counters);
 }
 
 // One pass over interactions [begin, begin + count) of the uploaded list, in a device-generated
@@ -1127,7 +1174,7 @@ extern "C" int lfm_plan_epoch(lfm_plan* p, const int32_t* shuffle_indices, uint3
 // interleave its own collectives between them.
 extern "C" int lfm_plan_epoch_range(lfm_plan* p, uint32_t seed, int32_t num_threads, int64_t begin,
                                     int64_t count, lfm_counters* counters) {
-    return plan_epoch_impl(p, nullptr, seed, num_threads, begin, count, counters);
+    return plan_epoch_impl(p, nullptr, seed, num_threads, nullptr, begin, count, counters);
 }
 
 // ---- delta exchange of a replicated table (multi-GPU) -------------------------------

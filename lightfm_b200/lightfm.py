@@ -417,13 +417,18 @@ class LightFM(object):
         plan = cache.plan
         finite = True
         try:
-            for _ in self._progress(epochs, verbose=verbose):
-                # 625 words: one full Mersenne-Twister block, so get_state()[1] changes every
-                # epoch as it does under the reference's per-epoch shuffle
-                # (reference tests/test_movielens.py:669-682)
+            # One seed per epoch, drawn up front (the same draws in the same order as one per
+            # iteration: nothing else touches the RandomState in between), so that every epoch can tell
+            # the library the next one's seed and have its tuples packed while this one trains.
+            # 625 words each: one full Mersenne-Twister block, so get_state()[1] changes every epoch
+            # as it does under the reference's per-epoch shuffle (reference tests/test_movielens.py:669-682)
+            seeds = []
+            for _ in range(epochs):
                 words = self.random_state.randint(0, np.iinfo(np.int32).max, size=625)
-                seed = int(np.bitwise_xor.reduce(words.astype(np.uint32) * np.uint32(2654435761)))
-                plan.epoch(seed, num_threads=max(2, num_threads))
+                seeds.append(int(np.bitwise_xor.reduce(words.astype(np.uint32) * np.uint32(2654435761))))
+            for e in self._progress(epochs, verbose=verbose):
+                plan.epoch(seeds[e], num_threads=max(2, num_threads),
+                           next_seed=seeds[e + 1] if e + 1 < epochs else None)
                 finite = plan.all_finite()   # the divergence check of L:447-464, on the device
                 if not finite:
                     break

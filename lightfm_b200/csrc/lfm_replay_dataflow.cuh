@@ -704,7 +704,7 @@ __global__ void __launch_bounds__(RDF_WARPS * 32) rdf_kernel(FitArgs a, RdfScrat
 static size_t rdf_scratch_bytes(int loss, const FitArgs& a, int64_t bitmap_limit_bytes) {
     const DevModel& m = a.model;
     if ((loss != LOSS_BPR && loss != LOSS_LOGISTIC) || !a.itf.identity || !a.usf.identity || a.item_alpha != 0.0 ||
-        a.user_alpha != 0.0 || m.d > 256 || m.d < 1 || a.n > 0x7fffffffLL || a.n < 1)
+        a.user_alpha != 0.0 || m.d > 256 || m.d < 1 || a.n > 0x7ff00000LL || a.n < 1)  // task indices are int32, with headroom for the executors' stride
         return 0;
     if (loss == LOSS_BPR && !a.pos.indptr) return 0;
     size_t b = 256 + sizeof(int32_t) * (2 * ((size_t)m.user.n + (size_t)m.item.n + 64) + 2 * (size_t)m.item.n) +
